@@ -1,0 +1,94 @@
+/* os2d_b200 - C ABI of the B200-native OS2D dense correlation-and-alignment head.
+ *
+ * The reference (aosokin/os2d) has no FFI: the hot path sits behind Python classes
+ * (os2d/modeling/head.py Os2dHead.forward :308-435, os2d/modeling/box_coder.py decode_pyramid :448-536).
+ * This header is the boundary a binding for that path uses; os2d_b200/_cabi.py is the ctypes binding that
+ * the drop-in Python classes (os2d_b200/head.py, box_coder.py) call.  Each entry point cites the reference
+ * code whose arithmetic it replaces.
+ *
+ * Conventions: plain device pointers and sizes, no allocation inside (the caller owns outputs and
+ * workspaces), stream-ordered on `stream` (a cudaStream_t passed as void*), re-entrant, return 0 on success
+ * or a negative error code; os2d_b200_last_error() gives a thread-local message for the last failure.
+ * All entry points require an sm_100 device (tcgen05 / TMA); there is no CPU or library fallback.
+ */
+#ifndef OS2D_B200_H_
+#define OS2D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OS2D_B200_OK 0
+#define OS2D_B200_ERR_BAD_ARG (-1)
+#define OS2D_B200_ERR_CUDA (-2)
+#define OS2D_B200_ERR_UNSUPPORTED (-3)
+#define OS2D_B200_ERR_DRIVER (-4)
+
+/* geometry constants of the packed layouts */
+#define OS2D_B200_GRID 15          /* template grid (head.py:66-69) */
+#define OS2D_B200_CORR_CH 225
+#define OS2D_B200_CORR_PAD 240     /* rows of the packed class operand, channels of the z volume */
+
+int os2d_b200_abi_version(void);
+const char* os2d_b200_last_error(void);
+/* number of SMs of the current device (persistent-grid size) */
+int os2d_b200_num_sms(void);
+
+/* ---- K0: operand preparation -------------------------------------------------------------------------
+ * Class side (head.py:241-259 resize to 15x15, :293 L2 norm, :342-344 transposed channel order):
+ *   maps   [C, D, h, w] fp32 (all classes of one call share h, w)
+ *   cf32   [C, D, 15, 15] fp32  - the normalised maps the reference keeps in Os2dHead.class_feature_maps
+ *   packed [C, 240, D] fp16     - GEMM operand, row k = tx*15 + ty, rows 225..239 zero, values * 32
+ *   normalize = 0 returns the resized maps without the L2 normalisation (head.py:241-259 alone). */
+int os2d_pack_class_features(const float* maps, int C, int D, int h, int w, int normalize, float* cf32, void* packed,
+                             void* stream);
+/* Image side (head.py:339): fm [B, D, N] fp32 -> packed [B, N, D] fp16 (values * 32 / (norm + 1e-5)).
+ * inv_ws: workspace of B*N floats. */
+int os2d_pack_image_features(const float* fm, int B, int D, int N, float* inv_ws, void* packed, void* stream);
+
+/* ---- K1: correlation + ReLU/L2-norm epilogue (head.py:342-350, :650) ---------------------------------
+ *   zvol   [B*C, 30, H*W, 8] fp16  centred/normalised correlation + DC side channels (conv1 operand)
+ *   rawvol [B*C, 225, H*W]  fp16  correlation values (sampler input) */
+int os2d_correlate(const void* img_packed, const void* cls_packed, int B, int C, int D, int H, int W, void* zvol,
+                   void* rawvol, void* stream);
+
+/* ---- K2: TransformNet convolution layers (head.py:604-655) -------------------------------------------
+ * layer 1: 225(+DC)->128 k7, BN+ReLU; layer 2: 128->64 k5 (hi/lo weight rows), BN+ReLU; layer 3: 64->P k5.
+ * wblob: weights packed by os2d_b200.head.pack_transform_net (shared-memory image, see csrc/conv.cu);
+ * alpha/beta: 128 floats each (folded BN scale/shift incl. operand pre-scales).
+ * in/out volumes: fp16 [planes, chunks8, H*W, 8]; layer 3 writes fp32 [planes, P, H*W]. */
+size_t os2d_conv_weight_blob_bytes(int ksize, int in_chunks16);
+int os2d_transform_conv(int layer, int out_real, const void* in_vol, const void* wblob, const float* alpha,
+                        const float* beta, void* out, int planes, int H, int W, void* stream);
+
+/* ---- K3: affine grid + bilinear resample/pool + box regression (head.py:81-193, 371-433, 439-520) -----
+ *   params [planes, P, H*W] fp32 (P = 6 affine, 4 simplified), inverse: use_inverse_geom_model
+ *   score [planes, H*W], loc [planes, 4, H*W], corners [planes, 8, H*W] with caller-given plane strides
+ *   (in floats) so the outputs can live inside one gather buffer. */
+int os2d_resample_boxes(const void* rawvol, const float* params, int planes, int P, int H, int W, int inverse,
+                        float stride_w, float stride_h, float box_w, float box_h, float* score, float* loc,
+                        float* corners, long long score_plane_stride, long long loc_plane_stride,
+                        long long corners_plane_stride, void* stream);
+
+/* ---- K4: decode + filter, all classes of one pyramid level (box_coder.py:490-520) ---------------------
+ *   loc [C,4,N], score [C,N], corners [C,8,N] or NULL -> boxes [C,N,4], anchors [N,4], corners_out [C,N,8],
+ *   valid [C,N] (score > thr and non-empty after clipping); boxes/anchors/corners are rescaled to the
+ *   original image (BoxList.resize, bounding_box.py:138-163). */
+int os2d_decode_boxes(int C, int N, int fm_w, float stride_w, float stride_h, float box_w, float box_h, float img_w,
+                      float img_h, float score_thr, float scale_x, float scale_y, int same_scale, const float* loc,
+                      const float* score, const float* corners, float* boxes, float* anchors, float* corners_out,
+                      uint8_t* valid, void* stream);
+
+/* ---- K5: batched greedy NMS (bounding_box.py:344-387 per chunk, torchvision nms semantics) -------------
+ *   boxes [M,4]; order [total] candidate indices, each segment sorted by score descending;
+ *   seg_offsets [num_segs+1]; every segment <= 10000 boxes; keep [total] (1 = survives) in `order` positions. */
+int os2d_nms_segments(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int num_segs,
+                      double iou_threshold, uint8_t* keep, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OS2D_B200_H_ */

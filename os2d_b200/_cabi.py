@@ -1,0 +1,86 @@
+"""ctypes binding of the C ABI declared in include/os2d_b200.h (libos2d_b200.so, built in-tree).
+
+There is deliberately no fallback: if the shared library is missing or an entry point fails, the
+caller gets an exception.  PyTorch is only used by the callers for device memory and streams.
+"""
+import ctypes
+import os
+
+_LIB_NAME = "libos2d_b200.so"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+_c_int = ctypes.c_int
+_c_float = ctypes.c_float
+_c_void_p = ctypes.c_void_p
+_c_ll = ctypes.c_longlong
+
+# name -> (restype, argtypes); mirrors include/os2d_b200.h one to one
+SIGNATURES = {
+    "os2d_b200_abi_version": (_c_int, []),
+    "os2d_b200_last_error": (ctypes.c_char_p, []),
+    "os2d_b200_num_sms": (_c_int, []),
+    "os2d_pack_class_features": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
+                                          _c_void_p]),
+    "os2d_pack_image_features": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
+    "os2d_correlate": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
+                                _c_void_p]),
+    "os2d_conv_weight_blob_bytes": (ctypes.c_size_t, [_c_int, _c_int]),
+    "os2d_transform_conv": (_c_int, [_c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
+                                     _c_int, _c_int, _c_void_p]),
+    "os2d_resample_boxes": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float,
+                                     _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_ll, _c_ll,
+                                     _c_void_p]),
+    "os2d_decode_boxes": (_c_int, [_c_int, _c_int, _c_int, _c_float, _c_float, _c_float, _c_float, _c_float, _c_float,
+                                   _c_float, _c_float, _c_float, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                   _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "os2d_nms_segments": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, ctypes.c_double, _c_void_p, _c_void_p]),
+}
+
+
+class Os2dB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def library_path():
+    return os.path.join(_HERE, _LIB_NAME)
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise Os2dB200Error(
+            "{} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C os2d_b200/csrc` (no CPU or library fallback exists)".format(path))
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the symbol is missing
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().os2d_b200_last_error()
+        raise Os2dB200Error("{} failed with code {}: {}".format(what, rc, msg.decode() if msg else ""))
+
+
+def ptr(t):
+    """Device pointer of a (contiguous) torch tensor, or None."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "os2d_b200 kernels take contiguous tensors"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,147 @@
+// extern "C" shim of include/os2d_b200.h + host utilities (error string, tensor-map encoder).
+#include <cudaTypedefs.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/os2d_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace os2d {
+
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* what, cudaError_t e) {
+  snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+void set_last_error_msg(const char* what) { snprintf(g_err, sizeof(g_err), "%s", what); }
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) {
+    set_last_error_msg("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed");
+    return nullptr;
+  }
+  fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  return fn;
+}
+
+int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                      const uint32_t* box, CUtensorMapSwizzle swizzle, CUtensorMapL2promotion promo) {
+  auto fn = get_encode_fn();
+  if (!fn) return kErrDriver;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr,
+                  bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu, box %u %u %u)",
+             static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+             (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0);
+    return kErrDriver;
+  }
+  return kOk;
+}
+
+static int num_sms_cached() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (dev < 0 || dev >= 64) return -1;
+  if (cached[dev] == 0) {
+    int n = 0, major = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return -1;
+    if (major != 10) {
+      set_last_error_msg("os2d_b200 requires a compute capability 10.x device (sm_100a kernels)");
+      return -1;
+    }
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace os2d
+
+using namespace os2d;
+
+extern "C" {
+
+int os2d_b200_abi_version(void) { return 1; }
+const char* os2d_b200_last_error(void) { return os2d::g_err; }
+int os2d_b200_num_sms(void) { return num_sms_cached(); }
+
+int os2d_pack_class_features(const float* maps, int C, int D, int h, int w, int normalize, float* cf32, void* packed,
+                             void* stream) {
+  if (!maps || !cf32 || !packed) return kErrBadArg;
+  return launch_pack_class(maps, C, D, h, w, normalize, cf32, packed, static_cast<cudaStream_t>(stream));
+}
+
+int os2d_pack_image_features(const float* fm, int B, int D, int N, float* inv_ws, void* packed, void* stream) {
+  if (!fm || !inv_ws || !packed) return kErrBadArg;
+  return launch_pack_image(fm, B, D, N, inv_ws, packed, static_cast<cudaStream_t>(stream));
+}
+
+int os2d_correlate(const void* img_packed, const void* cls_packed, int B, int C, int D, int H, int W, void* zvol,
+                   void* rawvol, void* stream) {
+  if (!img_packed || !cls_packed || !zvol || !rawvol) return kErrBadArg;
+  const int sms = num_sms_cached();
+  if (sms <= 0) return kErrUnsupported;
+  return launch_corr(img_packed, cls_packed, B, C, D, H, W, zvol, rawvol, sms, static_cast<cudaStream_t>(stream));
+}
+
+size_t os2d_conv_weight_blob_bytes(int ksize, int in_chunks16) { return conv_weight_blob_bytes(ksize, in_chunks16); }
+
+int os2d_transform_conv(int layer, int out_real, const void* in_vol, const void* wblob, const float* alpha,
+                        const float* beta, void* out, int planes, int H, int W, void* stream) {
+  if (!in_vol || !wblob || !alpha || !beta || !out) return kErrBadArg;
+  const int sms = num_sms_cached();
+  if (sms <= 0) return kErrUnsupported;
+  ConvLayerDesc L;
+  L.lo_scale = 1.0f / 2048.0f;
+  if (layer == 1) { L.ksize = 7; L.in_chunks16 = kCorrPad / 16; L.out_real = 128; L.mode = 0; }
+  else if (layer == 2) { L.ksize = 5; L.in_chunks16 = 8; L.out_real = 64; L.mode = 1; }
+  else if (layer == 3) { L.ksize = 5; L.in_chunks16 = 4; L.out_real = out_real; L.mode = 2; }
+  else return kErrBadArg;
+  if (layer == 3 && (out_real < 1 || out_real > 64)) return kErrBadArg;
+  return launch_conv(L, in_vol, wblob, alpha, beta, out, planes, H, W, sms, static_cast<cudaStream_t>(stream));
+}
+
+int os2d_resample_boxes(const void* rawvol, const float* params, int planes, int P, int H, int W, int inverse,
+                        float stride_w, float stride_h, float box_w, float box_h, float* score, float* loc,
+                        float* corners, long long score_plane_stride, long long loc_plane_stride,
+                        long long corners_plane_stride, void* stream) {
+  if (!rawvol || !params || !score || !loc || !corners) return kErrBadArg;
+  return launch_resample(rawvol, params, planes, P, H, W, inverse, stride_w, stride_h, box_w, box_h, score, loc, corners,
+                         score_plane_stride, loc_plane_stride, corners_plane_stride, static_cast<cudaStream_t>(stream));
+}
+
+int os2d_decode_boxes(int C, int N, int fm_w, float stride_w, float stride_h, float box_w, float box_h, float img_w,
+                      float img_h, float score_thr, float scale_x, float scale_y, int same_scale, const float* loc,
+                      const float* score, const float* corners, float* boxes, float* anchors, float* corners_out,
+                      uint8_t* valid, void* stream) {
+  if (!loc || !score || !boxes || !anchors || !valid) return kErrBadArg;
+  if (corners && !corners_out) return kErrBadArg;
+  DecodeArgs A;
+  A.C = C; A.N = N; A.fm_w = fm_w;
+  A.stride_w = stride_w; A.stride_h = stride_h; A.box_w = box_w; A.box_h = box_h;
+  A.img_w = img_w; A.img_h = img_h; A.score_thr = score_thr;
+  A.scale_x = scale_x; A.scale_y = scale_y; A.same_scale = same_scale;
+  return launch_decode(A, loc, score, corners, boxes, anchors, corners_out, valid, static_cast<cudaStream_t>(stream));
+}
+
+int os2d_nms_segments(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int num_segs,
+                      double iou_threshold, uint8_t* keep, void* stream) {
+  if (num_segs < 0) return kErrBadArg;
+  if (num_segs == 0) return kOk;
+  if (!boxes || !order || !seg_offsets || !keep) return kErrBadArg;
+  return launch_nms(boxes, order, seg_offsets, num_segs, iou_threshold, keep, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

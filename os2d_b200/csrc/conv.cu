@@ -1,0 +1,316 @@
+// K2: the TransformNet convolutions as tcgen05 implicit GEMMs (reference: os2d/modeling/head.py:604-655,
+// conv 225->128 k7 p3 + BN + ReLU, conv 128->64 k5 p2 + BN + ReLU, conv 64->P k5 p2).
+//
+// Formulation:  D[cout (M = 128 TMEM lanes), pixel (N <= 256 columns)] += W[tap][cout, ci] * X[pixel + tap, ci]
+//   * A operand (weights): packed on the host into the exact shared-memory image
+//     [sub-chunk of 16 ci][dy][dx][2 x 8-channel K groups][128 rows][8 ci] fp16, streamed with 1-D bulk copies
+//     (one kernel row = KS taps per ring stage).  No-swizzle K-major core matrices (8 rows x 16 B).
+//   * B operand (activations): volume layout [plane][chunk8][H][W][8 ci] fp16.  One TMA box per 16-channel
+//     sub-chunk brings the halo (16 + 2 pad) x (32 + 2 pad) pixels of a 2-strip tile into shared memory as
+//     [2][rows][cols][16 B]; zero padding of the convolution = TMA out-of-bounds fill.  Every tap is then a
+//     *shifted view* of the same halo: the UMMA descriptor start address moves by (dy * cols + dx) * 16 B,
+//     SBO = cols * 16 B (one image row of an 8-pixel-wide strip per 8-row core-matrix group).
+//   * a CTA tile = 2 strips (8 px wide, up to 32 rows) => two N<=256 accumulators = all 512 TMEM columns;
+//     every weight byte fetched from L2 is used for 512 pixels.
+// Epilogue modes: see ConvLayerDesc in kernels.h (BN folded to fp32 alpha/beta, hi/lo weight rows combined).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace os2d {
+namespace conv {
+
+constexpr int THREADS = 256;
+constexpr int NUM_H = 2;   // halo ring depth
+constexpr int NUM_W = 4;   // weight ring depth
+constexpr uint32_t TAP_BYTES = 2 * 128 * 16;   // one tap, 16 input channels: [2][128 rows][16 B]
+constexpr uint32_t TRANS_STRIDE = 32 * 16 + 16;  // per-warp transpose staging: chunk stride (bank skew)
+constexpr uint32_t TRANS_BYTES = 4 * TRANS_STRIDE;  // per warp
+constexpr uint32_t COMB_STRIDE = 33;                // floats per row in the hi/lo combine staging
+constexpr uint32_t COMB_BYTES = 64 * COMB_STRIDE * 4;
+
+template <int KS>
+struct Geo {
+  static constexpr int PAD = KS / 2;
+  static constexpr int HWX = kStripW * kStripsPerTile + 2 * PAD;   // halo columns
+  static constexpr int HWY = kMaxTileRows + 2 * PAD;               // halo rows (box height)
+  static constexpr uint32_t HALO_BYTES = 2u * HWY * HWX * 16u;
+  static constexpr uint32_t WSTAGE_BYTES = KS * TAP_BYTES;
+  static constexpr uint32_t SMEM_BYTES = NUM_H * HALO_BYTES + NUM_W * WSTAGE_BYTES + 4 * TRANS_BYTES + COMB_BYTES +
+                                         256 /*barriers*/ + 128 /*align*/;
+};
+
+struct Params {
+  int planes, H, W;
+  int T;              // rows per tile (even, <= 32)
+  int TY, TXP;        // tiles along y, strip pairs along x
+  int total_tiles;
+  int nsub;           // input channels / 16
+  int mode;
+  int out_real;
+  float lo_scale;
+  const uint8_t* wblob;
+  const float* alpha;
+  const float* beta;
+  void* out;
+};
+
+template <int KS>
+__global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant__ CUtensorMap map_in, Params P) {
+  using G = Geo<KS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* halo = smem;
+  uint8_t* wst = halo + NUM_H * G::HALO_BYTES;
+  uint8_t* trans = wst + NUM_W * G::WSTAGE_BYTES;
+  float* comb = reinterpret_cast<float*>(trans + 4 * TRANS_BYTES);
+  uint64_t* hfull = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(comb) + COMB_BYTES);
+  uint64_t* hempty = hfull + NUM_H;
+  uint64_t* wfull = hempty + NUM_H;
+  uint64_t* wempty = wfull + NUM_W;
+  uint64_t* tfull = wempty + NUM_W;
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&map_in);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NUM_H; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1); }
+    for (int i = 0; i < NUM_W; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_plane = P.TY * P.TXP;
+
+  if (warp == 0) {
+    // ------------------------------ producer: halo boxes (TMA) + weight rows (bulk) ------------------------------
+    if (lane == 0) {
+      int hs = 0; uint32_t hph = 0;
+      int ws = 0; uint32_t wph = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        const int plane = t / tiles_per_plane;
+        const int rem = t - plane * tiles_per_plane;
+        const int ty = rem / P.TXP, txp = rem - ty * P.TXP;
+        const int y0 = ty * P.T, x0 = txp * (kStripW * kStripsPerTile);
+        for (int sc = 0; sc < P.nsub; ++sc) {
+          mbar_wait(&hempty[hs], hph ^ 1);
+          mbar_expect_tx(&hfull[hs], G::HALO_BYTES);
+          tma_load_4d(halo + hs * G::HALO_BYTES, &map_in, &hfull[hs], 8 * (x0 - G::PAD), y0 - G::PAD, 2 * sc, plane);
+          if (++hs == NUM_H) { hs = 0; hph ^= 1; }
+          for (int dy = 0; dy < KS; ++dy) {
+            mbar_wait(&wempty[ws], wph ^ 1);
+            mbar_expect_tx(&wfull[ws], G::WSTAGE_BYTES);
+            bulk_load_1d(wst + ws * G::WSTAGE_BYTES, P.wblob + static_cast<size_t>(sc * KS + dy) * G::WSTAGE_BYTES,
+                         G::WSTAGE_BYTES, &wfull[ws]);
+            if (++ws == NUM_W) { ws = 0; wph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      int hs = 0; uint32_t hph = 0;
+      int ws = 0; uint32_t wph = 0;
+      uint32_t tph = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        const int plane = t / tiles_per_plane;
+        const int rem = t - plane * tiles_per_plane;
+        const int ty = rem / P.TXP, txp = rem - ty * P.TXP;
+        const int y0 = ty * P.T, x0 = txp * (kStripW * kStripsPerTile);
+        int rows = min(P.T, P.H - y0);
+        rows = (rows + 1) & ~1;
+        const int nstrips = (x0 + kStripW < P.W) ? 2 : 1;
+        const uint32_t idesc = umma_idesc_f16(128, rows * kStripW);
+
+        mbar_wait(tempty, tph ^ 1);   // epilogue has drained the accumulators of the previous tile
+        tc_fence_after();
+        for (int sc = 0; sc < P.nsub; ++sc) {
+          mbar_wait(&hfull[hs], hph);
+          tc_fence_after();
+          const uint32_t hbase = smem_u32(halo + hs * G::HALO_BYTES);
+          for (int dy = 0; dy < KS; ++dy) {
+            mbar_wait(&wfull[ws], wph);
+            tc_fence_after();
+            const uint32_t wbase = smem_u32(wst + ws * G::WSTAGE_BYTES);
+#pragma unroll
+            for (int dx = 0; dx < KS; ++dx) {
+              const uint64_t da = umma_smem_desc(wbase + dx * TAP_BYTES, /*LBO (K group)*/ 128 * 16, /*SBO*/ 128, 0);
+              const uint32_t acc = (sc | dy | dx) != 0;
+              for (int s = 0; s < nstrips; ++s) {
+                const uint32_t bstart = hbase + static_cast<uint32_t>((dy * G::HWX + dx + kStripW * s) * 16);
+                const uint64_t db = umma_smem_desc(bstart, /*LBO*/ G::HWY * G::HWX * 16, /*SBO*/ G::HWX * 16, 0);
+                umma_f16(tmem_base + s * 256, da, db, idesc, acc);
+              }
+            }
+            umma_commit(&wempty[ws]);
+            if (++ws == NUM_W) { ws = 0; wph ^= 1; }
+          }
+          umma_commit(&hempty[hs]);
+          if (++hs == NUM_H) { hs = 0; hph ^= 1; }
+        }
+        umma_commit(tfull);
+        tph ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const int e = warp - 4;
+    const int row = e * 32 + lane;                 // accumulator row = output channel (or hi/lo row)
+    uint8_t* my_trans = trans + e * TRANS_BYTES;
+    float alpha = 0.f, beta = 0.f;
+    if (P.mode == 0 || row < 64) { alpha = P.alpha[row]; beta = P.beta[row]; }
+    uint32_t tph = 0;
+    const size_t HW = static_cast<size_t>(P.H) * P.W;
+    const int out_chunks = (P.mode == 0) ? 16 : 8;
+    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+      const int plane = t / tiles_per_plane;
+      const int rem = t - plane * tiles_per_plane;
+      const int ty = rem / P.TXP, txp = rem - ty * P.TXP;
+      const int y0 = ty * P.T, x0 = txp * (kStripW * kStripsPerTile);
+      const int rows = min(P.T, P.H - y0);
+      const int nstrips = (x0 + kStripW < P.W) ? 2 : 1;
+      const int nquads = (rows + 3) >> 2;
+
+      mbar_wait(tfull, tph);
+      tc_fence_after();
+      for (int s = 0; s < nstrips; ++s) {
+        for (int rq = 0; rq < nquads; ++rq) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + s * 256 + rq * 32 + (static_cast<uint32_t>(e * 32) << 16), r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+
+          if (P.mode != 0) {
+            // combine hi rows (0..63) with lo rows (64..127): lo warps publish, hi warps consume
+            if (e >= 2) {
+              float* dst = comb + (row - 64) * COMB_STRIDE;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) dst[j] = v[j];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (e < 2) {
+              const float* src = comb + row * COMB_STRIDE;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaf(src[j], P.lo_scale, v[j]);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
+
+          // pixel j of this block: image row y0 + 4*rq + j/8, column x0 + 8*s + j%8
+          if (P.mode == 2) {
+            if (row < P.out_real) {
+              float* o = reinterpret_cast<float*>(P.out) + (static_cast<size_t>(plane) * P.out_real + row) * HW;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int y = y0 + 4 * rq + (j >> 3), x = x0 + kStripW * s + (j & 7);
+                if (y < P.H && (4 * rq + (j >> 3)) < rows && x < P.W) o[static_cast<size_t>(y) * P.W + x] = fmaf(alpha, v[j], beta);
+              }
+            }
+          } else if (P.mode == 0 || e < 2) {
+            // BN + ReLU -> fp16, transpose 32 channels x 32 pixels through shared memory
+            const uint32_t cl = lane >> 3, pos = lane & 7;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const __half hv = __float2half(fmaxf(fmaf(alpha, v[j], beta), 0.f));
+              *reinterpret_cast<__half*>(my_trans + cl * TRANS_STRIDE + j * 16 + pos * 2) = hv;
+            }
+            __syncwarp();
+            const int y = y0 + 4 * rq + (lane >> 3), x = x0 + kStripW * s + (lane & 7);
+            const bool ok = (4 * rq + (lane >> 3)) < rows && x < P.W;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 val = *reinterpret_cast<const uint4*>(my_trans + q * TRANS_STRIDE + lane * 16);
+              if (ok) {
+                __half* o = reinterpret_cast<__half*>(P.out) +
+                            ((static_cast<size_t>(plane) * out_chunks + (e * 4 + q)) * HW + static_cast<size_t>(y) * P.W + x) * 8;
+                *reinterpret_cast<uint4*>(o) = val;
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+      tph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+template <int KS>
+static int launch_t(const ConvLayerDesc& L, const void* in_vol, const void* wblob, const float* alpha,
+                    const float* beta, void* out, int planes, int H, int W, int num_sms, cudaStream_t st) {
+  using G = Geo<KS>;
+  const int in_chunks8 = L.in_chunks16 * 2;
+  CUtensorMap map_in;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(8) * W, static_cast<uint64_t>(H), static_cast<uint64_t>(in_chunks8),
+                        static_cast<uint64_t>(planes)};
+    uint64_t strides[3] = {static_cast<uint64_t>(16) * W, static_cast<uint64_t>(16) * W * H,
+                           static_cast<uint64_t>(16) * W * H * in_chunks8};
+    uint32_t box[4] = {static_cast<uint32_t>(8 * G::HWX), static_cast<uint32_t>(G::HWY), 2, 1};
+    int rc = encode_tensor_map(&map_in, in_vol, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (rc != kOk) return rc;
+  }
+  Params P;
+  P.planes = planes; P.H = H; P.W = W;
+  const int nty = (H + kMaxTileRows - 1) / kMaxTileRows;
+  int T = (H + nty - 1) / nty;
+  T = (T + 1) & ~1;
+  P.T = T;
+  P.TY = (H + T - 1) / T;
+  P.TXP = (W + kStripW * kStripsPerTile - 1) / (kStripW * kStripsPerTile);
+  P.total_tiles = planes * P.TY * P.TXP;
+  P.nsub = L.in_chunks16;
+  P.mode = L.mode;
+  P.out_real = L.out_real;
+  P.lo_scale = L.lo_scale;
+  P.wblob = reinterpret_cast<const uint8_t*>(wblob);
+  P.alpha = alpha;
+  P.beta = beta;
+  P.out = out;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OS2D_CUDA_TRY(cudaFuncSetAttribute(conv_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = P.total_tiles < num_sms ? P.total_tiles : num_sms;
+  conv_kernel<KS><<<grid, THREADS, G::SMEM_BYTES, st>>>(map_in, P);
+  OS2D_CUDA_TRY(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace conv
+
+size_t conv_weight_blob_bytes(int ksize, int in_chunks16) {
+  return static_cast<size_t>(in_chunks16) * ksize * ksize * conv::TAP_BYTES;
+}
+
+int launch_conv(const ConvLayerDesc& L, const void* in_vol, const void* wblob, const float* alpha, const float* beta,
+                void* out, int planes, int H, int W, int num_sms, cudaStream_t st) {
+  if (planes <= 0 || H <= 0 || W <= 0 || L.in_chunks16 <= 0 || L.mode < 0 || L.mode > 2) return kErrBadArg;
+  if ((static_cast<uint64_t>(16) * W) % 16 != 0) return kErrBadArg;
+  if (L.ksize == 7) return conv::launch_t<7>(L, in_vol, wblob, alpha, beta, out, planes, H, W, num_sms, st);
+  if (L.ksize == 5) return conv::launch_t<5>(L, in_vol, wblob, alpha, beta, out, planes, H, W, num_sms, st);
+  return kErrUnsupported;
+}
+
+}  // namespace os2d

@@ -1,0 +1,66 @@
+// Internal launcher declarations + layout constants shared by the kernels and the C ABI shim.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace os2d {
+
+// geometry of the OS2D head (os2d/modeling/head.py:66-69)
+constexpr int kGrid = 15;                 // template grid 15 x 15
+constexpr int kCorrCh = kGrid * kGrid;    // 225 correlation channels
+constexpr int kCorrPad = 240;             // padded to a multiple of 16 (MMA N / K granularity)
+constexpr int kZChunks = kCorrPad / 8;    // 30 chunks of 8 channels in the z volume
+constexpr int kDcCh = 225;                // first of the 3 DC side channels (mean hi, mean hi, mean lo)
+
+// power-of-two operand pre-scales (exact in fp16/fp32; undone in the epilogues)
+constexpr float kScaleFeat = 32.0f;       // L2-normalised features -> fp16
+constexpr float kScaleZ = 64.0f;          // centred normalised correlation (z - mean) -> fp16
+constexpr float kScaleMean = 8.0f;        // per-pixel mean of z -> fp16 hi/lo pair
+
+// ---- conv implicit-GEMM tile geometry (conv.cu) ----
+constexpr int kStripW = 8;                // a strip is 8 pixels wide
+constexpr int kStripsPerTile = 2;         // two adjacent strips share one halo box
+constexpr int kMaxTileRows = 32;          // 8 * 32 = 256 = max MMA N
+
+int launch_pack_class(const float* maps, int C, int D, int h, int w, int normalize, float* cf32, void* packed,
+                      cudaStream_t st);
+int launch_pack_image(const float* fm, int B, int D, int N, float* inv_ws, void* packed, cudaStream_t st);
+
+// correlation GEMM + ReLU/L2norm/centering epilogue
+int launch_corr(const void* img_packed, const void* cls_packed, int B, int C, int D, int H, int W, void* zvol,
+                void* rawvol, int num_sms, cudaStream_t st);
+
+// implicit-GEMM convolution layer of the TransformNet.  layer: 1, 2, 3
+struct ConvLayerDesc {
+  int ksize;          // 7 or 5
+  int in_chunks16;    // input channels / 16 (15, 8, 4)
+  int out_real;       // real output channels (128, 64, P)
+  int mode;           // 0: relu(alpha*acc+beta) -> fp16 chunk8 volume (128 rows)
+                      // 1: combine hi/lo rows (c, c+64), relu(alpha*acc+beta) -> fp16 chunk8 volume (64 ch)
+                      // 2: combine hi/lo rows, alpha*acc+beta -> fp32 planar [plane][out_real][H][W]
+  float lo_scale;     // factor applied to the lo-row accumulator before adding (2^-11) in modes 1/2
+};
+int launch_conv(const ConvLayerDesc& L, const void* in_vol, const void* wblob, const float* alpha, const float* beta,
+                void* out, int planes, int H, int W, int num_sms, cudaStream_t st);
+
+int launch_resample(const void* rawvol, const float* params, int planes, int P, int H, int W, int inverse,
+                    float stride_w, float stride_h, float box_w, float box_h, float* score, float* loc,
+                    float* corners, long long score_ps, long long loc_ps, long long corners_ps, cudaStream_t st);
+
+// post-processing
+struct DecodeArgs {
+  int C, N, fm_w;                 // classes, anchors (= fm_h * fm_w), feature-map width
+  float stride_w, stride_h, box_w, box_h;   // anchor grid
+  float img_w, img_h;             // clip window (pyramid-level image size)
+  float score_thr;                // keep score > thr (strict)
+  float scale_x, scale_y;         // level -> original image (BoxList.resize), 1 when no inverse transform
+  int same_scale;                 // ratio_w == ratio_h branch of BoxList.resize (single multiply)
+};
+int launch_decode(const DecodeArgs& A, const float* loc, const float* score, const float* corners, float* boxes,
+                  float* anchors_out, float* corners_out, uint8_t* valid, cudaStream_t st);
+int launch_nms(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int num_segs, double iou_thr,
+               uint8_t* keep, cudaStream_t st);
+
+size_t conv_weight_blob_bytes(int ksize, int in_chunks16);
+
+}  // namespace os2d

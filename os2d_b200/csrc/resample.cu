@@ -1,0 +1,117 @@
+// K3: affine grid generation + bilinear resample/pool of the correlation volume + box regression, one thread
+// per (image, class, location); the [.,H,W,15,15,2] grid tensors of the reference are never materialised.
+//   theta assembly / inverse     os2d/modeling/head.py:81-153
+//   grid = theta * (x_j, y_i, 1) os2d/modeling/head.py:184   (F.affine_grid, align_corners=True)
+//   local -> feature-map coords  os2d/modeling/head.py:18-40, 371-384  (px = 7.5 gx + x + 0.5, clamped)
+//   resample + masked mean       os2d/modeling/head.py:439-520 (inner 11x11 points, channel k = j*15 + i)
+//   box / corners / loc          os2d/modeling/head.py:404-433, box_coder.py:306-317, bounding_box.py:267-277
+// Lanes run along x so that the 4 taps of a grid point are near-coalesced reads of one channel plane.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace os2d {
+
+__device__ __forceinline__ float lin15(int i) {
+  const float step = 2.0f / 14.0f;
+  return (i < 7) ? (-1.0f + step * i) : (1.0f - step * (14 - i));
+}
+
+__global__ void __launch_bounds__(128) resample_kernel(const __half* __restrict__ raw, const float* __restrict__ params,
+                                                        int P, int H, int W, int inverse, float stride_w,
+                                                        float stride_h, float box_w, float box_h,
+                                                        float* __restrict__ score, float* __restrict__ loc,
+                                                        float* __restrict__ corners, long long score_ps,
+                                                        long long loc_ps, long long corners_ps) {
+  const int N = H * W;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int plane = blockIdx.y;
+  if (pix >= N) return;
+  const int y = pix / W, x = pix - y * W;
+  const float* pp = params + static_cast<size_t>(plane) * P * N + pix;
+  float a, b, tx, c, d, ty;
+  if (P == 6) {
+    a = pp[0]; b = pp[N]; tx = pp[2 * N]; c = pp[3 * static_cast<size_t>(N)]; d = pp[4 * static_cast<size_t>(N)];
+    ty = pp[5 * static_cast<size_t>(N)];
+  } else {
+    a = pp[0]; b = 0.f; tx = pp[N]; c = 0.f; d = pp[2 * N]; ty = pp[3 * static_cast<size_t>(N)];
+  }
+  if (inverse) {
+    const float det = a * d - b * c;
+    const float ia = d / det, ib = -b / det, ic = -c / det, id = a / det;
+    const float itx = -(ia * tx + ib * ty), ity = -(ic * tx + id * ty);
+    a = ia; b = ib; c = ic; d = id; tx = itx; ty = ity;
+  }
+
+  // ---- score: mean of bilinear samples at the inner 11 x 11 grid points ----
+  const __half* rplane = raw + static_cast<size_t>(plane) * kCorrCh * N;
+  const float cx0 = x + 0.5f, cy0 = y + 0.5f;
+  const float xmax = static_cast<float>(W - 1), ymax = static_cast<float>(H - 1);
+  float acc = 0.f;
+#pragma unroll 1
+  for (int j = 2; j <= 12; ++j) {          // template x index
+    const float xj = lin15(j);
+    const float gx_j = fmaf(a, xj, tx), gy_j = fmaf(c, xj, ty);
+#pragma unroll
+    for (int i = 2; i <= 12; ++i) {        // template y index
+      const float yi = lin15(i);
+      const float gx = fmaf(b, yi, gx_j), gy = fmaf(d, yi, gy_j);
+      float px = fminf(fmaxf(fmaf(gx, 7.5f, cx0), 0.f), xmax);
+      float py = fminf(fmaxf(fmaf(gy, 7.5f, cy0), 0.f), ymax);
+      const float fx0 = floorf(px), fy0 = floorf(py);
+      const float wx = px - fx0, wy = py - fy0;
+      const int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0);
+      const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+      const __half* ch = rplane + static_cast<size_t>(j * kGrid + i) * N;
+      const float v00 = __half2float(ch[y0 * W + x0]), v01 = __half2float(ch[y0 * W + x1]);
+      const float v10 = __half2float(ch[y1 * W + x0]), v11 = __half2float(ch[y1 * W + x1]);
+      const float top = fmaf(wx, v01 - v00, v00), bot = fmaf(wx, v11 - v10, v10);
+      acc += fmaf(wy, bot - top, top);
+    }
+  }
+  score[static_cast<size_t>(plane) * score_ps + pix] = acc * (1.0f / 121.0f);
+
+  // ---- box = bbox of the transformed grid (extremes are at the 4 corner points), corners, loc ----
+  // anchor: centre (x + 0.5) * stride, size box (240 = 16 * 14 + 16 for the ResNet C4 backbones, head.py:216-238)
+  const float acx = (x + 0.5f) * stride_w, acy = (y + 0.5f) * stride_h;
+  const float hbw = 0.5f * box_w, hbh = 0.5f * box_h;
+  float X[4], Y[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float yi = (q & 2) ? 1.0f : -1.0f;   // i = 0 / 14
+    const float xj = (q & 1) ? 1.0f : -1.0f;   // j = 0 / 14
+    const float gx = a * xj + b * yi + tx, gy = c * xj + d * yi + ty;
+    X[q] = fmaf(gx, hbw, acx);
+    Y[q] = fmaf(gy, hbh, acy);
+  }
+  float* co = corners + static_cast<size_t>(plane) * corners_ps + pix;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    co[static_cast<size_t>(2 * q) * N] = X[q];
+    co[static_cast<size_t>(2 * q + 1) * N] = Y[q];
+  }
+  const float x1 = fminf(fminf(X[0], X[1]), fminf(X[2], X[3])), y1 = fminf(fminf(Y[0], Y[1]), fminf(Y[2], Y[3]));
+  float x2 = fmaxf(fmaxf(X[0], X[1]), fmaxf(X[2], X[3])), y2 = fmaxf(fmaxf(Y[0], Y[1]), fmaxf(Y[2], Y[3]));
+  if (x1 + 1.0f > x2) x2 = x1 + 1.0f;
+  if (y1 + 1.0f > y2) y2 = y1 + 1.0f;
+  const float gw = x2 - x1, gh = y2 - y1;
+  const float gcx = x1 + 0.5f * gw, gcy = y1 + 0.5f * gh;
+  float* lo = loc + static_cast<size_t>(plane) * loc_ps + pix;
+  lo[0] = 10.0f * (gcx - acx) / box_w;
+  lo[N] = 10.0f * (gcy - acy) / box_h;
+  lo[2 * static_cast<size_t>(N)] = 5.0f * logf(gw / box_w);
+  lo[3 * static_cast<size_t>(N)] = 5.0f * logf(gh / box_h);
+}
+
+int launch_resample(const void* rawvol, const float* params, int planes, int P, int H, int W, int inverse,
+                    float stride_w, float stride_h, float box_w, float box_h, float* score, float* loc,
+                    float* corners, long long score_ps, long long loc_ps, long long corners_ps, cudaStream_t st) {
+  if (planes <= 0 || (P != 4 && P != 6) || H < 2 || W < 2) return kErrBadArg;
+  const int N = H * W;
+  resample_kernel<<<dim3((N + 127) / 128, planes), 128, 0, st>>>(reinterpret_cast<const __half*>(rawvol), params, P, H,
+                                                              W, inverse, stride_w, stride_h, box_w, box_h, score, loc,
+                                                              corners, score_ps, loc_ps, corners_ps);
+  OS2D_CUDA_TRY(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace os2d

@@ -1,0 +1,374 @@
+"""Drop-in replacements of the reference head classes (os2d/modeling/head.py) whose arithmetic runs in
+the sm_100a kernels behind the C ABI (include/os2d_b200.h):
+
+    build_os2d_head_creator  head.py:12     TransformationNet  head.py:604
+    Os2dAlignment            head.py:43     Os2dHeadCreator    head.py:204     Os2dHead  head.py:271
+
+Constructor signatures, attribute names and state-dict keys
+(``aligner.parameter_regressor.{conv.0,conv.1,conv.3,conv.4,linear}.*``) match the reference so reference
+checkpoints load unchanged and ``Os2dModel`` can own an ``Os2dHeadCreator`` of this module.
+
+Inference only: the kernels implement the eval-mode forward (BatchNorm running statistics, no autograd).
+Calling the head with gradients required or BatchNorm in training mode raises - there is no PyTorch / CPU
+fallback path in this package.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from .structures import FeatureMapSize
+from .box_coder import BoxGridGenerator
+
+GRID = 15
+CORR_CH = GRID * GRID
+CORR_PAD = 240
+Z_CHUNKS = CORR_PAD // 8
+SCALE_Z = 64.0
+SCALE_MEAN = 8.0
+LO_SCALE = 2048.0
+DC_CH = 225
+
+
+def build_os2d_head_creator(do_simple_affine, is_cuda, use_inverse_geom_model, feature_map_stride,
+                            feature_map_receptive_field):
+    """Same factory as the reference (head.py:12-15)."""
+    aligner = Os2dAlignment(do_simple_affine, is_cuda, use_inverse_geom_model)
+    return Os2dHeadCreator(aligner, feature_map_stride, feature_map_receptive_field)
+
+
+def _pow2_scale(t):
+    """Power of two s such that max|t| * s lies in [0.5, 1) (exact rescale for fp16 storage)."""
+    m = float(t.abs().max())
+    if not math.isfinite(m) or m <= 0.0:
+        return 1.0
+    return 2.0 ** (-math.floor(math.log2(m)) - 1)
+
+
+def _to_blob(wp, ks):
+    """[128 rows, ci_pad (multiple of 16), ks, ks] fp32 -> shared-memory image consumed by csrc/conv.cu:
+    [sub-chunk(16 ci)][dy][dx][k-group(8 ci)][row][8 ci] fp16."""
+    rows, ci_pad = wp.shape[0], wp.shape[1]
+    assert rows == 128 and ci_pad % 16 == 0
+    v = wp.view(128, ci_pad // 16, 2, 8, ks, ks).permute(1, 4, 5, 2, 0, 3).contiguous()
+    return v.to(torch.float16).contiguous()
+
+
+class TransformationNet(nn.Module):
+    """Parameter regression network, same modules / state-dict keys as the reference (head.py:604-661):
+    conv = [Conv2d(225,128,7,p3), BN, ReLU, Conv2d(128,64,5,p2), BN, ReLU], linear = Conv2d(64,P,5,p2),
+    last layer initialised to the identity transform (head.py:631-642)."""
+
+    def __init__(self, output_dim=6, use_cuda=True, normalization='batchnorm', kernel_sizes=[7, 5], channels=[128, 64],
+                 input_feature_dim=15 * 15, num_groups=16):
+        super(TransformationNet, self).__init__()
+        if normalization.lower() != 'batchnorm' or list(kernel_sizes) != [7, 5] or list(channels) != [128, 64] \
+                or input_feature_dim != CORR_CH or output_dim not in (4, 6):
+            raise NotImplementedError("os2d_b200 kernels implement the OS2D TransformNet (225->128 k7, 128->64 k5, "
+                                      "64->{4,6} k5, batchnorm) only")
+        mods = []
+        ch_in = input_feature_dim
+        for ch_out, k in zip(channels, kernel_sizes):
+            mods += [nn.Conv2d(ch_in, ch_out, kernel_size=k, padding=k // 2), nn.BatchNorm2d(ch_out), nn.ReLU(inplace=True)]
+            ch_in = ch_out
+        self.conv = nn.Sequential(*mods)
+        self.linear = nn.Conv2d(ch_in, output_dim, kernel_size=(kernel_sizes[-1], kernel_sizes[-1]),
+                                padding=kernel_sizes[-1] // 2)
+        with torch.no_grad():
+            self.linear.weight.zero_()
+            self.linear.bias.zero_()
+            self.linear.bias[0] = 1
+            self.linear.bias[4 if output_dim == 6 else 2] = 1
+        self.output_dim = output_dim
+        if use_cuda:
+            self.conv.cuda()
+            self.linear.cuda()
+        self._packed = None
+        self._packed_key = None
+
+    def freeze_bn(self):
+        for layer in self.modules():
+            if isinstance(layer, nn.BatchNorm2d):
+                layer.eval()
+
+    # ---- weight folding / packing for the kernels (one-time per weight version) ----
+    def _version_key(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def packed_weights(self):
+        """BN-folded, fp16-packed operands of the three conv kernels (cached until a parameter changes)."""
+        key = self._version_key()
+        if self._packed is not None and self._packed_key == key:
+            return self._packed
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d) and m.training:
+                raise RuntimeError("os2d_b200: BatchNorm of the TransformNet is in training mode; the kernels implement "
+                                   "the eval-mode forward only (call .eval() / freeze_bn())")
+        self._packed = pack_transform_net(self.state_dict(), self.output_dim, self.linear.weight.device)
+        self._packed_key = key
+        return self._packed
+
+    def forward(self, corr_maps):
+        raise NotImplementedError("os2d_b200.TransformationNet runs fused inside Os2dHead.forward (the fp32 correlation "
+                                  "volume it would take as input is never materialised)")
+
+
+def pack_transform_net(sd, out_dim, device):
+    """Fold eval-mode BatchNorm into fp32 epilogue scale/shift and pack the conv weights for csrc/conv.cu.
+
+    layer 1: rows = 128 output channels; input channels 0..224 = W1 * s1 (fp16); the K1 epilogue stores the
+             *centred* z, so the per-pixel mean enters through DC side channels 225..227 carrying
+             V[co,tap] = sum_ci W1 * s1 * 64 / 8 split into fp16 hi/lo (mean is split hi/lo as well).
+    layer 2: rows 0..63 = fp16(W2 * s2), rows 64..127 = fp16 residual * 2048 (combined in the epilogue).
+    layer 3: rows 0..P-1 = fp16(W3 * s3), rows 64..64+P-1 = fp16 residual * 2048.
+    """
+    f32 = dict((k, v.detach().to(device="cpu", dtype=torch.float64)) for k, v in sd.items() if v.dtype.is_floating_point)
+    eps = 1e-5
+
+    def bn_fold(conv, bn):
+        a = f32[bn + ".weight"] / torch.sqrt(f32[bn + ".running_var"] + eps)
+        b = (f32[conv + ".bias"] - f32[bn + ".running_mean"]) * a + f32[bn + ".bias"]
+        return a, b
+
+    out = {}
+    # ---- layer 1 ----
+    w1 = f32["conv.0.weight"]                      # [128,225,7,7]
+    s1 = _pow2_scale(w1)
+    wp = torch.zeros(128, CORR_PAD, 7, 7, dtype=torch.float64)
+    wp[:, :CORR_CH] = w1 * s1
+    v = w1.sum(dim=1) * (s1 * SCALE_Z / SCALE_MEAN)   # [128,7,7]
+    vh = v.to(torch.float16).to(torch.float64)
+    vl = (v - vh)
+    wp[:, DC_CH] = vh
+    wp[:, DC_CH + 1] = vl
+    wp[:, DC_CH + 2] = vh
+    a1, b1 = bn_fold("conv.0", "conv.1")
+    out["w1"] = _to_blob(wp.float(), 7).to(device)
+    out["alpha1"] = (a1 / (s1 * SCALE_Z)).float().to(device).contiguous()
+    out["beta1"] = b1.float().to(device).contiguous()
+    # ---- layer 2 ----
+    w2 = f32["conv.3.weight"]                      # [64,128,5,5]
+    s2 = _pow2_scale(w2)
+    w2s = w2 * s2
+    w2h = w2s.to(torch.float16).to(torch.float64)
+    wp = torch.zeros(128, 128, 5, 5, dtype=torch.float64)
+    wp[:64] = w2h
+    wp[64:] = (w2s - w2h) * LO_SCALE
+    a2, b2 = bn_fold("conv.3", "conv.4")
+    pad = torch.zeros(64, dtype=torch.float64)
+    out["w2"] = _to_blob(wp.float(), 5).to(device)
+    out["alpha2"] = torch.cat([a2 / s2, pad]).float().to(device).contiguous()
+    out["beta2"] = torch.cat([b2, pad]).float().to(device).contiguous()
+    # ---- layer 3 ----
+    w3 = f32["linear.weight"]                      # [P,64,5,5]
+    s3 = _pow2_scale(w3)
+    w3s = w3 * s3
+    w3h = w3s.to(torch.float16).to(torch.float64)
+    wp = torch.zeros(128, 64, 5, 5, dtype=torch.float64)
+    wp[:out_dim] = w3h
+    wp[64:64 + out_dim] = (w3s - w3h) * LO_SCALE
+    a3 = torch.zeros(128, dtype=torch.float64)
+    b3 = torch.zeros(128, dtype=torch.float64)
+    a3[:out_dim] = 1.0 / s3
+    b3[:out_dim] = f32["linear.bias"]
+    out["w3"] = _to_blob(wp.float(), 5).to(device)
+    out["alpha3"] = a3.float().to(device).contiguous()
+    out["beta3"] = b3.float().to(device).contiguous()
+    return out
+
+
+class Os2dAlignment(nn.Module):
+    """Transformation model: owns the parameter regressor and the transform conventions (head.py:43-193).
+    The grid generation itself (prepare_transform_parameters_for_grid_sampler + F.affine_grid, head.py:81-193)
+    is fused into the resample kernel (csrc/resample.cu)."""
+
+    def __init__(self, do_simple_affine, is_cuda, use_inverse_geom_model):
+        super(Os2dAlignment, self).__init__()
+        self.model_type = "affine" if not do_simple_affine else "simple_affine"
+        self.use_inverse_geom_model = use_inverse_geom_model
+        transform_net_output_dim = 6 if self.model_type == "affine" else 4
+        self.out_grid_size = FeatureMapSize(w=GRID, h=GRID)
+        self.reference_feature_map_size = FeatureMapSize(w=GRID, h=GRID)
+        self.network_stride = FeatureMapSize(w=1, h=1)
+        self.network_receptive_field = FeatureMapSize(w=GRID, h=GRID)
+        self.input_feature_dim = self.reference_feature_map_size.w * self.reference_feature_map_size.h
+        self.parameter_regressor = TransformationNet(output_dim=transform_net_output_dim, use_cuda=is_cuda,
+                                                     normalization='batchnorm', kernel_sizes=[7, 5], channels=[128, 64],
+                                                     input_feature_dim=self.input_feature_dim)
+
+    def forward(self, corr_maps):
+        raise NotImplementedError("os2d_b200.Os2dAlignment is fused into Os2dHead.forward; the "
+                                  "[N,H,W,15,15,2] grid tensor of the reference is never materialised")
+
+
+class Os2dHeadCreator(nn.Module):
+    """Creates Os2dHead instances from class feature maps; owns the trainable aligner (head.py:204-268)."""
+
+    def __init__(self, aligner, feature_map_stride, feature_map_receptive_field):
+        super(Os2dHeadCreator, self).__init__()
+        self.aligner = aligner
+        rec_field, stride = self.get_rec_field_and_stride_after_concat_nets(
+            feature_map_receptive_field, feature_map_stride, self.aligner.network_receptive_field, self.aligner.network_stride)
+        self.box_grid_generator_image_level = BoxGridGenerator(box_size=rec_field, box_stride=stride)
+        self.box_grid_generator_feature_map_level = BoxGridGenerator(box_size=self.aligner.network_receptive_field,
+                                                                     box_stride=self.aligner.network_stride)
+
+    @staticmethod
+    def get_rec_field_and_stride_after_concat_nets(receptive_field_netA, stride_netA, receptive_field_netB, stride_netB):
+        """Receptive field / stride of netB(netA(x)) (head.py:222-238)."""
+        if hasattr(receptive_field_netA, "w"):
+            rf_w, st_w = Os2dHeadCreator.get_rec_field_and_stride_after_concat_nets(
+                receptive_field_netA.w, stride_netA.w, receptive_field_netB.w, stride_netB.w)
+            rf_h, st_h = Os2dHeadCreator.get_rec_field_and_stride_after_concat_nets(
+                receptive_field_netA.h, stride_netA.h, receptive_field_netB.h, stride_netB.h)
+            return FeatureMapSize(w=rf_w, h=rf_h), FeatureMapSize(w=st_w, h=st_h)
+        return stride_netA * (receptive_field_netB - 1) + receptive_field_netA, stride_netA * stride_netB
+
+    @staticmethod
+    def resize_feature_maps_to_reference_size(ref_size, feature_maps):
+        """Bilinear resize of every class map to 15x15 (head.py:240-259); returns the un-normalised fp32 maps."""
+        cf32, _ = _prepare_class_operands(feature_maps, normalized=False)
+        return cf32
+
+    def create_os2d_head(self, class_feature_maps):
+        return Os2dHead(class_feature_maps, self.aligner, self.box_grid_generator_image_level,
+                        self.box_grid_generator_feature_map_level, _from_raw_maps=True)
+
+
+def _prepare_class_operands(feature_maps, normalized=True):
+    """list of [1,D,h,w] CUDA fp32 maps -> (cf32 [C,D,15,15], packed fp16 [C,240,D]) via os2d_pack_class_features.
+    Classes are grouped by (h, w) so that each group is one kernel launch."""
+    lib = _cabi.load()
+    assert len(feature_maps) > 0
+    dev = feature_maps[0].device
+    if dev.type != "cuda":
+        raise RuntimeError("os2d_b200 requires CUDA tensors (no CPU path)")
+    D = feature_maps[0].size(1)
+    C = len(feature_maps)
+    cf32 = torch.empty(C, D, GRID, GRID, dtype=torch.float32, device=dev)
+    packed = torch.empty(C, CORR_PAD, D, dtype=torch.float16, device=dev)
+    groups = {}
+    for i, fm in enumerate(feature_maps):
+        assert fm.size(0) == 1, "Can process only batches of size 1, but have {0}".format(fm.size(0))
+        assert fm.size(1) == D
+        groups.setdefault((fm.size(2), fm.size(3)), []).append(i)
+    for (h, w), idx in groups.items():
+        maps = torch.cat([feature_maps[i] for i in idx], dim=0).to(dtype=torch.float32).contiguous()
+        g_cf = torch.empty(len(idx), D, GRID, GRID, dtype=torch.float32, device=dev)
+        g_pk = torch.empty(len(idx), CORR_PAD, D, dtype=torch.float16, device=dev)
+        rc = lib.os2d_pack_class_features(_cabi.ptr(maps), len(idx), D, h, w, 1 if normalized else 0, _cabi.ptr(g_cf),
+                                          _cabi.ptr(g_pk), _cabi.stream_ptr())
+        _cabi.check(rc, "os2d_pack_class_features")
+        ii = torch.tensor(idx, device=dev)
+        cf32.index_copy_(0, ii, g_cf)
+        packed.index_copy_(0, ii, g_pk)
+    return cf32, packed
+
+
+class Os2dHead(nn.Module):
+    """Recognition + localisation scores of a batch of class feature maps against image feature maps
+    (head.py:271-435).  ``forward`` has the reference signature and return tuple."""
+
+    def __init__(self, class_feature_maps, aligner, box_grid_generator_image_level, box_grid_generator_feature_map_level,
+                 pool_border_width=2, _from_raw_maps=False):
+        super(Os2dHead, self).__init__()
+        if pool_border_width != 2:
+            raise NotImplementedError("the resample kernel pools the inner 11x11 grid points (pool_border_width=2)")
+        if _from_raw_maps:
+            maps = list(class_feature_maps)
+        else:
+            # reference constructor contract: an already resized [C,D,15,15] tensor (head.py:277-293)
+            maps = [class_feature_maps[i:i + 1] for i in range(class_feature_maps.size(0))]
+        cf32, packed = _prepare_class_operands(maps)
+        self.class_feature_maps = cf32           # L2-normalised, as in head.py:293
+        self._class_packed = packed
+        self.class_batch_size = cf32.size(0)
+        self.box_grid_generator_image_level = box_grid_generator_image_level
+        self.box_grid_generator_feature_map_level = box_grid_generator_feature_map_level
+        mask = torch.zeros(self.class_batch_size, 1, GRID, GRID, dtype=torch.float32, device=cf32.device)
+        mask[:, :, pool_border_width:GRID - pool_border_width, pool_border_width:GRID - pool_border_width] = 1
+        self.class_pool_mask = mask / mask.sum(dim=(2, 3), keepdim=True)     # head.py:295-302
+        self.aligner = aligner
+        self.max_planes_per_call = 4096
+
+    def forward(self, feature_maps):
+        """feature_maps [B,D,H,W] -> (loc [B,C,4,H,W], rec [B,C,1,H,W], rec_transform_detached (same tensor under
+        no-grad, head.py:400-402), corners [B,C,8,H,W])."""
+        if torch.is_grad_enabled() and (feature_maps.requires_grad or
+                                        any(p.requires_grad for p in self.aligner.parameters())):
+            raise RuntimeError("os2d_b200.Os2dHead implements inference only; call it under torch.no_grad() "
+                               "(training / autograd through the head is out of scope and has no fallback)")
+        if feature_maps.device.type != "cuda":
+            raise RuntimeError("os2d_b200 requires CUDA tensors (no CPU path)")
+        B, D, H, W = feature_maps.shape
+        assert D == self.class_feature_maps.size(1), \
+            "Feature dimensionality of input={0} and class={1} feature maps has to equal".format(D, self.class_feature_maps.size(1))
+        if H < 2 or W < 2:
+            raise ValueError("feature map must be at least 2x2 (the reference divides by W-1, H-1: head.py:381-382)")
+        C = self.class_batch_size
+        dev = feature_maps.device
+        lib = _cabi.load()
+        st = _cabi.stream_ptr()
+        N = H * W
+        pw = self.aligner.parameter_regressor.packed_weights()
+        P = self.aligner.parameter_regressor.output_dim
+        inverse = 1 if self.aligner.use_inverse_geom_model else 0
+        gen = self.box_grid_generator_image_level
+
+        fm = feature_maps.detach().to(dtype=torch.float32).contiguous()
+        img_packed = torch.empty(B, N, D, dtype=torch.float16, device=dev)
+        inv_ws = torch.empty(B, N, dtype=torch.float32, device=dev)
+        _cabi.check(lib.os2d_pack_image_features(_cabi.ptr(fm), B, D, N, _cabi.ptr(inv_ws), _cabi.ptr(img_packed), st),
+                    "os2d_pack_image_features")
+
+        loc = torch.empty(B, C, 4, H, W, dtype=torch.float32, device=dev)
+        score = torch.empty(B, C, 1, H, W, dtype=torch.float32, device=dev)
+        corners = torch.empty(B, C, 8, H, W, dtype=torch.float32, device=dev)
+
+        # class chunks bound the workspace (z / raw / hidden volumes); classes are independent in eval mode
+        cmax = max(1, self.max_planes_per_call // B)
+        for c0 in range(0, C, cmax):
+            cc = min(cmax, C - c0)
+            planes = B * cc
+            zvol = torch.empty(planes, Z_CHUNKS, N, 8, dtype=torch.float16, device=dev)
+            rawvol = torch.empty(planes, CORR_CH, N, dtype=torch.float16, device=dev)
+            h1 = torch.empty(planes, 16, N, 8, dtype=torch.float16, device=dev)
+            h2 = torch.empty(planes, 8, N, 8, dtype=torch.float16, device=dev)
+            params = torch.empty(planes, P, N, dtype=torch.float32, device=dev)
+            cls = self._class_packed[c0:c0 + cc]
+            _cabi.check(lib.os2d_correlate(_cabi.ptr(img_packed), _cabi.ptr(cls), B, cc, D, H, W, _cabi.ptr(zvol),
+                                           _cabi.ptr(rawvol), st), "os2d_correlate")
+            _cabi.check(lib.os2d_transform_conv(1, 128, _cabi.ptr(zvol), _cabi.ptr(pw["w1"]), _cabi.ptr(pw["alpha1"]),
+                                                _cabi.ptr(pw["beta1"]), _cabi.ptr(h1), planes, H, W, st), "os2d_transform_conv(1)")
+            _cabi.check(lib.os2d_transform_conv(2, 64, _cabi.ptr(h1), _cabi.ptr(pw["w2"]), _cabi.ptr(pw["alpha2"]),
+                                                _cabi.ptr(pw["beta2"]), _cabi.ptr(h2), planes, H, W, st), "os2d_transform_conv(2)")
+            _cabi.check(lib.os2d_transform_conv(3, P, _cabi.ptr(h2), _cabi.ptr(pw["w3"]), _cabi.ptr(pw["alpha3"]),
+                                                _cabi.ptr(pw["beta3"]), _cabi.ptr(params), planes, H, W, st), "os2d_transform_conv(3)")
+            if cc == C:
+                o_loc, o_score, o_corners = loc, score, corners
+            else:
+                o_loc = torch.empty(B, cc, 4, H, W, dtype=torch.float32, device=dev)
+                o_score = torch.empty(B, cc, 1, H, W, dtype=torch.float32, device=dev)
+                o_corners = torch.empty(B, cc, 8, H, W, dtype=torch.float32, device=dev)
+            _cabi.check(lib.os2d_resample_boxes(_cabi.ptr(rawvol), _cabi.ptr(params), planes, P, H, W, inverse,
+                                                float(gen.box_stride.w), float(gen.box_stride.h), float(gen.box_size.w),
+                                                float(gen.box_size.h), _cabi.ptr(o_score), _cabi.ptr(o_loc),
+                                                _cabi.ptr(o_corners), N, 4 * N, 8 * N, st), "os2d_resample_boxes")
+            if cc != C:
+                loc[:, c0:c0 + cc] = o_loc
+                score[:, c0:c0 + cc] = o_score
+                corners[:, c0:c0 + cc] = o_corners
+        return loc, score, score, corners
+
+    @staticmethod
+    def resample_of_correlation_map_fast(corr_maps, resampling_grids_grid_coord, class_pool_mask):
+        raise NotImplementedError("fused into Os2dHead.forward (csrc/resample.cu); the explicit-grid entry point of the "
+                                  "reference (head.py:439-520) has no standalone kernel")
+
+    resample_of_correlation_map_simple = resample_of_correlation_map_fast
+
+
+def normalize_feature_map_L2(feature_maps, epsilon=1e-6):
+    """x / (||x||_2 over dim 1 + eps) (head.py:597-601); tensor utility kept for API compatibility."""
+    return feature_maps / (feature_maps.norm(dim=1, keepdim=True) + epsilon)
