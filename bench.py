@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the OS2D head hot path (BASELINE.json metric: query-classes/sec at 1280 px input).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation (oracle port), rank 0
+
+A step = one pass of the hot path over one batch of synthetic input: image feature map [B,1024,80,80] (1280 px
+input through a stride-16 C4 backbone, which is outside the path) against C query classes, V2 head
+(affine + inverse): image L2-norm/pack -> correlation -> TransformNet -> resample/pool -> loc/corners
+(+ the all-gather of per-class outputs when N > 1).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "query-classes/sec at 1280px input"
+UNIT = "classes/s"
+D = 1024
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--classes", type=int, default=100, help="query classes per GPU (weak scaling)")
+    ap.add_argument("--size", type=int, default=1280, help="input image side in pixels")
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--cpu-sample-classes", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    fm = -(-args.size // 16)
+    return {
+        "workload": "configs[1]: {0}px synthetic input ({1}x{1}x1024 C4 feature map), {2} query classes per GPU, "
+                    "ResNet-C4 feature dim 1024, V2 inverse-geom affine head".format(args.size, fm, args.classes),
+        "classes_per_gpu": args.classes, "global_classes": args.classes * n_gpus, "batch": args.batch,
+        "feature_map": [fm, fm], "parallelism": "class-sharded x{}".format(n_gpus),
+        "cache": "inputs larger than L2: every step streams ~{:.2f} GB of intermediate volumes per GPU".format(
+            args.batch * args.classes * fm * fm * (480 + 450 + 256 + 128 + 24 + 52) / 1e9),
+    }
+
+
+def synth(args, device, seed):
+    """Synthetic features of the config's shape (no dataset / checkpoint offline): ReLU'd Gaussians like C4 outputs."""
+    g = torch.Generator().manual_seed(seed)
+    fm = -(-args.size // 16)
+    cms = (torch.randn(args.classes, D, 15, 15, generator=g) * 0.5 + 0.2).relu()
+    fmap = (torch.randn(args.batch, D, fm, fm, generator=g) * 0.5 + 0.2).relu()
+    return cms, fmap
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md): nvidia-smi during the timed region
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU implementation, all host threads
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(args, steps, warmup, sample_classes):
+    from oracle import head_oracle as ho
+    torch.set_num_threads(os.cpu_count())
+    g = torch.Generator().manual_seed(0)
+    fm = -(-args.size // 16)
+    cms = [(torch.randn(1, D, 15, 15, generator=g) * 0.5 + 0.2).relu() for _ in range(sample_classes)]
+    fmap = (torch.randn(args.batch, D, fm, fm, generator=g) * 0.5 + 0.2).relu()
+    tn = ho.random_transform_net(6, seed=1, spread=0.005)
+    cf = ho.prepare_class_features(cms)
+    with torch.no_grad():
+        for _ in range(warmup):
+            ho.head_forward(cf, fmap, tn, False, True, class_chunk=sample_classes)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ho.head_forward(cf, fmap, tn, False, True, class_chunk=sample_classes)
+        dt = time.perf_counter() - t0
+    rate = args.batch * sample_classes * steps / dt
+    sample = "{} steps x {} classes x batch {} at {}x{} feature map (oracle port of Os2dHead.forward, torch CPU fp32, {} threads)".format(
+        steps, sample_classes, args.batch, fm, fm, torch.get_num_threads())
+    return rate, dt / steps * 1e3, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_classes = max(1, min(args.cpu_sample_classes, args.classes))
+    steps = max(1, args.steps)
+    rate, ms, sample = cpu_reference_rate(args, steps, max(1, min(args.warmup, 2)), sample_classes)
+    cfg = workload_config(args, args.gpus)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from os2d_b200 import head as bh
+    from os2d_b200 import dist as bd
+    from os2d_b200.structures import FeatureMapSize
+    from oracle import head_oracle as ho   # only for the seeded TransformNet weights and the cpu_baseline leg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node {}".format(args.gpus)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    fm_side = -(-args.size // 16)
+    N = fm_side * fm_side
+    B, C = args.batch, args.classes
+    cms, fmap = synth(args, dev, seed=1234 + rank)
+    tn = ho.random_transform_net(6, seed=1, spread=0.005)
+    hc = bh.build_os2d_head_creator(False, True, True, FeatureMapSize(w=16, h=16), FeatureMapSize(w=16, h=16))
+    hc.aligner.parameter_regressor.load_state_dict(dict(tn), strict=False)
+    hc.eval()
+    with torch.no_grad():
+        head = hc.create_os2d_head([cms[i:i + 1].to(dev) for i in range(C)])
+    fm_host = fmap.pin_memory()
+    fm_dev = fmap.to(dev)
+    gather = bd.allocate_gather_buffer(B, C * world, N, world, dev) if world > 1 else None
+
+    def step(fm_d):
+        with torch.no_grad():
+            loc, score, _, corners = head(fm_d)
+            if world > 1:
+                s_v, l_v, c_v = bd.local_views(gather, rank)
+                s_v.copy_(score.view(B, C, 1, N)); l_v.copy_(loc.view(B, C, 4, N)); c_v.copy_(corners.view(B, C, 8, N))
+                bd.all_gather_outputs(gather)
+        return loc, score, corners
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident throughput (value) ----
+    for _ in range(args.warmup):
+        step(fm_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    head.profile_events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(fm_dev)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    stage_ms = {}
+    for name, a, b in head.profile_events:
+        stage_ms.setdefault(name, []).append(a.elapsed_time(b))
+    head.profile_events = None
+    stage_avg = {k: sum(v) / len(v) for k, v in stage_ms.items()}
+    value = B * C * world * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public API with host buffers (e2e) ----
+    out_host = [torch.empty(B, C, 4, fm_side, fm_side).pin_memory(), torch.empty(B, C, 1, fm_side, fm_side).pin_memory(),
+                torch.empty(B, C, 8, fm_side, fm_side).pin_memory()]
+    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    s_main = torch.cuda.current_stream()
+    fm_bufs = [torch.empty_like(fm_dev) for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_out_free = torch.cuda.Event()
+
+    def e2e_steps(n):
+        for i in range(n):
+            k = i % 2
+            with torch.cuda.stream(s_h2d):
+                if i >= 2:
+                    s_h2d.wait_event(ev_free[k])
+                fm_bufs[k].copy_(fm_host, non_blocking=True)
+                ev_in[k].record(s_h2d)
+            s_main.wait_event(ev_in[k])
+            loc, score, corners = step(fm_bufs[k])
+            ev_free[k].record(s_main)
+            done = torch.cuda.Event()
+            done.record(s_main)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(done)
+                for dst, src in zip(out_host, (loc, score, corners)):
+                    dst.copy_(src, non_blocking=True)
+                    src.record_stream(s_d2h)
+        s_main.wait_stream(s_d2h)
+
+    e2e_steps(max(2, args.warmup))
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    e2e_steps(args.steps)
+    f1.record()
+    barrier()
+    e2e_ms = max_over_ranks(f0.elapsed_time(f1))
+    e2e_value = B * C * world * args.steps / (e2e_ms * 1e-3)
+    h2d_bytes = fm_host.numel() * 4
+    d2h_bytes = sum(t.numel() for t in out_host) * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (conv1 of the TransformNet) + the correlation GEMM ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the step)" if peaks else "fallback 1.4 PF sustained"
+    planes = B * C
+    flop_conv1 = 2.0 * N * 225 * 128 * 49 * planes
+    flop_corr = 2.0 * N * 225 * D * planes
+    flop_conv2 = 2.0 * N * 128 * 64 * 25 * planes
+    flop_conv3 = 2.0 * N * 64 * 6 * 25 * planes
+
+    def roof(name, flop):
+        ms = stage_avg.get(name)
+        if not ms:
+            return None
+        ach = flop / (ms * 1e-3) / 1e12
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": None, "ms_per_launch": ms, "peak_source": peak_src}
+
+    roofline = roof("conv1", flop_conv1)
+    extra = {"roofline_corr": roof("corr", flop_corr), "roofline_conv2": roof("conv2", flop_conv2),
+             "roofline_conv3": roof("conv3", flop_conv3),
+             "stage_ms": stage_avg,
+             "tensor_frac_whole_step": (flop_conv1 + flop_corr + flop_conv2 + flop_conv3) * args.steps / (ms_total * 1e-3) / 1e12 / peak_tf}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        sc = max(1, min(args.cpu_sample_classes, C))
+        rate, _, sample = cpu_reference_rate(args, 3, 1, sc)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16 operands, fp32 accumulate (hi/lo-split weights)", "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": 7 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+    line.update(extra)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,91 @@
+"""Multi-GPU: shard the class (query) axis over the ranks of one node, one process per GPU.
+
+In eval mode every class's correlation / TransformNet / resample / box regression is independent
+(reference: per-class loop in os2d/engine/evaluate.py:323-327, per-class NMS box_coder.py:483-528), so the
+class axis partitions with no data-path exchange; the only collective is one all-gather of the per-class
+outputs before NMS (BASELINE.json north_star).  Each rank writes its class block [B, C_local, 13, N]
+(score 1 + loc 4 + corners 8 planes) directly into its slice of the gather buffer; the all-gather runs in
+place on that buffer (NCCL over NVLink on GPUs, gloo in the CPU unit tests).
+"""
+import torch
+import torch.distributed as dist
+
+OUT_PLANES = 13   # score(1) + loc(4) + corners(8)
+
+
+def shard_bounds(num_classes, world_size, rank):
+    """Contiguous block [lo, hi) of classes owned by ``rank``; blocks of ceil(C/world) classes (the last ranks may
+    own fewer or none)."""
+    per = -(-num_classes // world_size)
+    lo = min(rank * per, num_classes)
+    return lo, min(lo + per, num_classes)
+
+
+def padded_block(num_classes, world_size):
+    return -(-num_classes // world_size)
+
+
+def allocate_gather_buffer(B, num_classes, N, world_size, device):
+    """[world, B, per, 13, N] fp32: rank r's block is buffer[r]; classes beyond num_classes are padding."""
+    per = padded_block(num_classes, world_size)
+    return torch.zeros(world_size, B, per, OUT_PLANES, N, dtype=torch.float32, device=device)
+
+
+def local_views(buffer, rank):
+    """(score [B,per,1,N], loc [B,per,4,N], corners [B,per,8,N]) views of this rank's block."""
+    blk = buffer[rank]
+    return blk[:, :, 0:1], blk[:, :, 1:5], blk[:, :, 5:13]
+
+
+def all_gather_outputs(buffer, group=None):
+    """In-place all-gather of every rank's block of ``buffer`` ([world, ...])."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return buffer
+    rank = dist.get_rank(group)
+    dist.all_gather_into_tensor(buffer.view(-1), buffer[rank].reshape(-1).clone() if buffer.device.type == "cpu"
+                                else buffer[rank].reshape(-1), group=group)
+    return buffer
+
+
+def unpack_gathered(buffer, num_classes):
+    """[world,B,per,13,N] -> (loc [B,C,4,N], score [B,C,N], corners [B,C,8,N]) in global class order."""
+    world, B, per, _, N = buffer.shape
+    full = buffer.permute(1, 0, 2, 3, 4).reshape(B, world * per, OUT_PLANES, N)[:, :num_classes]
+    return full[:, :, 1:5], full[:, :, 0], full[:, :, 5:13]
+
+
+class ClassShardedHead:
+    """Runs an ``Os2dHead`` built from this rank's class block and all-gathers the per-class outputs.
+
+    ``head_factory(class_maps_block)`` creates the local head (normally
+    ``os2d_head_creator.create_os2d_head``); it is only called when the block is not empty.
+    """
+
+    def __init__(self, class_feature_maps, head_factory, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.num_classes = len(class_feature_maps)
+        lo, hi = shard_bounds(self.num_classes, self.world, self.rank)
+        self.lo, self.hi = lo, hi
+        self.head = head_factory(class_feature_maps[lo:hi]) if hi > lo else None
+
+    def forward(self, feature_maps):
+        B, _, H, W = feature_maps.shape
+        N = H * W
+        buf = allocate_gather_buffer(B, self.num_classes, N, self.world, feature_maps.device)
+        if self.head is not None:
+            loc, score, _, corners = self.head(feature_maps)
+            s_v, l_v, c_v = local_views(buf, self.rank)
+            n = self.hi - self.lo
+            s_v[:, :n].copy_(score.reshape(B, n, 1, N))
+            l_v[:, :n].copy_(loc.reshape(B, n, 4, N))
+            c_v[:, :n].copy_(corners.reshape(B, n, 8, N))
+        if self.world > 1:
+            all_gather_outputs(buf, self.group)
+        loc, score, corners = unpack_gathered(buf, self.num_classes)
+        return (loc.reshape(B, self.num_classes, 4, H, W), score.reshape(B, self.num_classes, 1, H, W),
+                corners.reshape(B, self.num_classes, 8, H, W))
+
+    __call__ = forward

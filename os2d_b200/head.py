@@ -291,6 +291,18 @@ class Os2dHead(nn.Module):
         self.class_pool_mask = mask / mask.sum(dim=(2, 3), keepdim=True)     # head.py:295-302
         self.aligner = aligner
         self.max_planes_per_call = 4096
+        # optional per-stage CUDA-event timing (bench.py): list of (stage, start_event, end_event) when not None
+        self.profile_events = None
+
+    def _timed(self, name, fn, *a):
+        if self.profile_events is None:
+            return fn(*a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*a)
+        e1.record()
+        self.profile_events.append((name, e0, e1))
+        return rc
 
     def forward(self, feature_maps):
         """feature_maps [B,D,H,W] -> (loc [B,C,4,H,W], rec [B,C,1,H,W], rec_transform_detached (same tensor under
@@ -319,8 +331,8 @@ class Os2dHead(nn.Module):
         fm = feature_maps.detach().to(dtype=torch.float32).contiguous()
         img_packed = torch.empty(B, N, D, dtype=torch.float16, device=dev)
         inv_ws = torch.empty(B, N, dtype=torch.float32, device=dev)
-        _cabi.check(lib.os2d_pack_image_features(_cabi.ptr(fm), B, D, N, _cabi.ptr(inv_ws), _cabi.ptr(img_packed), st),
-                    "os2d_pack_image_features")
+        _cabi.check(self._timed("pack_image", lib.os2d_pack_image_features, _cabi.ptr(fm), B, D, N, _cabi.ptr(inv_ws),
+                                _cabi.ptr(img_packed), st), "os2d_pack_image_features")
 
         loc = torch.empty(B, C, 4, H, W, dtype=torch.float32, device=dev)
         score = torch.empty(B, C, 1, H, W, dtype=torch.float32, device=dev)
@@ -337,24 +349,27 @@ class Os2dHead(nn.Module):
             h2 = torch.empty(planes, 8, N, 8, dtype=torch.float16, device=dev)
             params = torch.empty(planes, P, N, dtype=torch.float32, device=dev)
             cls = self._class_packed[c0:c0 + cc]
-            _cabi.check(lib.os2d_correlate(_cabi.ptr(img_packed), _cabi.ptr(cls), B, cc, D, H, W, _cabi.ptr(zvol),
-                                           _cabi.ptr(rawvol), st), "os2d_correlate")
-            _cabi.check(lib.os2d_transform_conv(1, 128, _cabi.ptr(zvol), _cabi.ptr(pw["w1"]), _cabi.ptr(pw["alpha1"]),
-                                                _cabi.ptr(pw["beta1"]), _cabi.ptr(h1), planes, H, W, st), "os2d_transform_conv(1)")
-            _cabi.check(lib.os2d_transform_conv(2, 64, _cabi.ptr(h1), _cabi.ptr(pw["w2"]), _cabi.ptr(pw["alpha2"]),
-                                                _cabi.ptr(pw["beta2"]), _cabi.ptr(h2), planes, H, W, st), "os2d_transform_conv(2)")
-            _cabi.check(lib.os2d_transform_conv(3, P, _cabi.ptr(h2), _cabi.ptr(pw["w3"]), _cabi.ptr(pw["alpha3"]),
-                                                _cabi.ptr(pw["beta3"]), _cabi.ptr(params), planes, H, W, st), "os2d_transform_conv(3)")
+            _cabi.check(self._timed("corr", lib.os2d_correlate, _cabi.ptr(img_packed), _cabi.ptr(cls), B, cc, D, H, W,
+                                    _cabi.ptr(zvol), _cabi.ptr(rawvol), st), "os2d_correlate")
+            _cabi.check(self._timed("conv1", lib.os2d_transform_conv, 1, 128, _cabi.ptr(zvol), _cabi.ptr(pw["w1"]),
+                                    _cabi.ptr(pw["alpha1"]), _cabi.ptr(pw["beta1"]), _cabi.ptr(h1), planes, H, W, st),
+                        "os2d_transform_conv(1)")
+            _cabi.check(self._timed("conv2", lib.os2d_transform_conv, 2, 64, _cabi.ptr(h1), _cabi.ptr(pw["w2"]),
+                                    _cabi.ptr(pw["alpha2"]), _cabi.ptr(pw["beta2"]), _cabi.ptr(h2), planes, H, W, st),
+                        "os2d_transform_conv(2)")
+            _cabi.check(self._timed("conv3", lib.os2d_transform_conv, 3, P, _cabi.ptr(h2), _cabi.ptr(pw["w3"]),
+                                    _cabi.ptr(pw["alpha3"]), _cabi.ptr(pw["beta3"]), _cabi.ptr(params), planes, H, W, st),
+                        "os2d_transform_conv(3)")
             if cc == C:
                 o_loc, o_score, o_corners = loc, score, corners
             else:
                 o_loc = torch.empty(B, cc, 4, H, W, dtype=torch.float32, device=dev)
                 o_score = torch.empty(B, cc, 1, H, W, dtype=torch.float32, device=dev)
                 o_corners = torch.empty(B, cc, 8, H, W, dtype=torch.float32, device=dev)
-            _cabi.check(lib.os2d_resample_boxes(_cabi.ptr(rawvol), _cabi.ptr(params), planes, P, H, W, inverse,
-                                                float(gen.box_stride.w), float(gen.box_stride.h), float(gen.box_size.w),
-                                                float(gen.box_size.h), _cabi.ptr(o_score), _cabi.ptr(o_loc),
-                                                _cabi.ptr(o_corners), N, 4 * N, 8 * N, st), "os2d_resample_boxes")
+            _cabi.check(self._timed("resample", lib.os2d_resample_boxes, _cabi.ptr(rawvol), _cabi.ptr(params), planes, P, H,
+                                    W, inverse, float(gen.box_stride.w), float(gen.box_stride.h), float(gen.box_size.w),
+                                    float(gen.box_size.h), _cabi.ptr(o_score), _cabi.ptr(o_loc), _cabi.ptr(o_corners),
+                                    N, 4 * N, 8 * N, st), "os2d_resample_boxes")
             if cc != C:
                 loc[:, c0:c0 + cc] = o_loc
                 score[:, c0:c0 + cc] = o_score

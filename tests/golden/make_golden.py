@@ -1,0 +1,143 @@
+"""Generates the golden input/output fixtures under tests/golden/ by running the UNMODIFIED reference
+(/root/reference/os2d, imported read-only) on seeded synthetic inputs.  Run in the build container:
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests or golden vectors for this path, so these files are the
+pin of the oracle: tests/test_oracle_golden.py checks oracle/ against them on any machine, and the GPU parity
+tests check the CUDA path against the same files.  The TransformNet weights are regenerated from a seed by
+oracle.head_oracle.random_transform_net (checksum stored in the fixture).
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+warnings.filterwarnings("ignore")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from os2d.modeling.head import build_os2d_head_creator          # noqa: E402  (the reference)
+from os2d.modeling.box_coder import Os2dBoxCoder                # noqa: E402
+from os2d.structures.feature_map import FeatureMapSize          # noqa: E402
+from os2d.structures.transforms import TransformList            # noqa: E402
+from os2d.structures.bounding_box import BoxList, nms as ref_nms  # noqa: E402
+from oracle import head_oracle as ho                            # noqa: E402
+
+D = 64
+TN_SEED = 11
+TN_SPREAD = 0.005
+VARIANTS = [("affine_inverse", False, True), ("affine", False, False), ("simple", True, False),
+            ("simple_inverse", True, True)]
+
+
+def tn_checksum(tn):
+    return float(sum(v.double().abs().sum() for v in tn.values()))
+
+
+def synth_inputs(seed, B, H, W, sizes):
+    g = torch.Generator().manual_seed(seed)
+    cms = [(torch.randn(1, D, h, w, generator=g) * 0.5 + 0.2).relu() for (h, w) in sizes]
+    fm = (torch.randn(B, D, H, W, generator=g) * 0.5 + 0.2).relu()
+    return cms, fm
+
+
+def ref_head(simple, inverse, tn, cms, fm):
+    hc = build_os2d_head_creator(simple, False, inverse, FeatureMapSize(w=16, h=16), FeatureMapSize(w=16, h=16))
+    sd = dict(tn)
+    sd["conv.1.num_batches_tracked"] = torch.tensor(0)
+    sd["conv.4.num_batches_tracked"] = torch.tensor(0)
+    hc.aligner.parameter_regressor.load_state_dict(sd)
+    hc.eval()
+    with torch.no_grad():
+        head = hc.create_os2d_head(cms)
+        loc, rec, _, corners = head(fm)
+    return hc, head, loc, rec, corners
+
+
+def make_head_goldens():
+    for name, simple, inverse in VARIANTS:
+        P = 4 if simple else 6
+        tn = ho.random_transform_net(P, seed=TN_SEED, spread=TN_SPREAD)
+        sizes = [(15, 15), (9, 17), (20, 8)]
+        cms, fm = synth_inputs(100 + P + int(inverse), 2, 13, 11, sizes)
+        hc, head, loc, rec, corners = ref_head(simple, inverse, tn, cms, fm)
+        out = {"fm": fm.numpy(), "loc": loc.numpy(), "score": rec.numpy(), "corners": corners.numpy(),
+               "class_features": head.class_feature_maps.numpy(),
+               "tn_seed": np.int64(TN_SEED), "tn_spread": np.float64(TN_SPREAD), "tn_checksum": np.float64(tn_checksum(tn)),
+               "simple": np.int64(simple), "inverse": np.int64(inverse)}
+        for i, c in enumerate(cms):
+            out["class_map_%d" % i] = c.numpy()
+        np.savez_compressed(os.path.join(HERE, "head_%s.npz" % name), **out)
+        print(name, "loc range", float(loc.min()), float(loc.max()), "score range", float(rec.min()), float(rec.max()))
+
+
+def make_decode_golden():
+    """Two pyramid levels, three class views with a duplicated class id, inverse transforms to a common size."""
+    simple, inverse = False, True
+    tn = ho.random_transform_net(6, seed=TN_SEED, spread=TN_SPREAD)
+    sizes = [(15, 15), (9, 17), (20, 8)]
+    img_sizes = [(176, 208), (240, 288)]          # (w, h) of the level images; fm = ceil(./16)
+    target = (480, 576)                           # common original image size (both ratios differ per level)
+    loc_pyr, cls_pyr, cor_pyr, fm_sizes = [], [], [], []
+    hc = None
+    for lvl, (iw, ih) in enumerate(img_sizes):
+        fw, fh = -(-iw // 16), -(-ih // 16)
+        cms, fm = synth_inputs(300 + lvl, 1, fh, fw, sizes)
+        if lvl > 0:
+            cms, _ = synth_inputs(300, 1, fh, fw, sizes)     # same class maps on every level
+        hc, head, loc, rec, corners = ref_head(simple, inverse, tn, cms, fm)
+        loc_pyr.append(loc[0].reshape(3, 4, -1))
+        cls_pyr.append(rec[0].reshape(3, -1))
+        cor_pyr.append(corners[0].reshape(3, 8, -1))
+        fm_sizes.append((fw, fh))
+    class_ids = [5, 7, 5]
+    box_coder = Os2dBoxCoder(0.5, 0.1, 0.8, 0.4, hc.box_grid_generator_image_level,
+                             lambda s: FeatureMapSize(w=-(-s.w // 16), h=-(-s.h // 16)), do_nms_across_classes=False)
+    tgt = FeatureMapSize(w=target[0], h=target[1])
+    transforms = []
+    for _ in img_sizes:
+        t = TransformList()
+        t.append(lambda boxes: boxes.resize(tgt))
+        transforms.append(t)
+    thr = float(torch.cat([c.flatten() for c in cls_pyr]).median())
+    res = box_coder.decode_pyramid(loc_pyr, cls_pyr, [FeatureMapSize(w=w, h=h) for (w, h) in img_sizes], class_ids,
+                                   nms_score_threshold=thr, nms_iou_threshold=0.3, inverse_box_transforms=transforms,
+                                   transform_corners_pyramid=cor_pyr)
+    out = {"class_ids": np.array(class_ids), "img_sizes": np.array(img_sizes), "fm_sizes": np.array(fm_sizes),
+           "target": np.array(target), "score_thr": np.float64(thr), "iou_thr": np.float64(0.3),
+           "boxes": res.bbox_xyxy.numpy(), "scores": res.get_field("scores").numpy(), "labels": res.get_field("labels").numpy(),
+           "default_boxes": res.get_field("default_boxes").bbox_xyxy.numpy(),
+           "transform_corners": res.get_field("transform_corners").numpy()}
+    for lvl in range(len(img_sizes)):
+        out["loc_%d" % lvl] = loc_pyr[lvl].numpy()
+        out["cls_%d" % lvl] = cls_pyr[lvl].numpy()
+        out["corners_%d" % lvl] = cor_pyr[lvl].numpy()
+    np.savez_compressed(os.path.join(HERE, "decode_pyramid.npz"), **out)
+    print("decode golden:", len(res), "detections, thr", thr)
+
+
+def make_nms_golden():
+    """Chunked NMS path (> 10000 candidates): only the seed and the kept indices are stored."""
+    seed, n = 77, 23000
+    g = torch.Generator().manual_seed(seed)
+    ctr = torch.rand(n, 2, generator=g) * 600
+    wh = torch.rand(n, 2, generator=g) * 120 + 20
+    boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], dim=1)
+    scores = (torch.rand(n, generator=g) * 64).round() / 64        # many exact ties
+    bl = BoxList(boxes, FeatureMapSize(w=800, h=800))
+    bl.add_field("scores", scores)
+    keep = ref_nms(bl, 0.3)
+    np.savez_compressed(os.path.join(HERE, "nms_chunked.npz"), seed=np.int64(seed), n=np.int64(n), keep=keep.numpy(),
+                        box_checksum=np.float64(boxes.double().sum()), score_checksum=np.float64(scores.double().sum()))
+    print("nms golden: kept", keep.numel(), "of", n)
+
+
+if __name__ == "__main__":
+    make_head_goldens()
+    make_decode_golden()
+    make_nms_golden()
