@@ -67,74 +67,93 @@ def synth(args, device, seed):
 # clocks sampling (B200_PROFILING.md): nvidia-smi during the timed region
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock / power / throttle reasons through NVML every 20 ms while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.samples, self.stop_flag, self.err = index, [], False, None
+        self.thread = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.smax = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:   # noqa: BLE001
+            self.err = repr(e)
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0, int(get_reasons(self.h))))
+            except Exception as e:   # noqa: BLE001
+                self.err = repr(e)
+                break
+            time.sleep(0.02)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons, power = [], None, set(), []
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power) if power else None}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: {}".format(self.err)]}
+        sm = sorted(s[0] for s in self.samples)
+        mask = 0
+        for s in self.samples:
+            mask |= s[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.smax, "reasons": sorted(v for k, v in self.REASONS.items() if mask & k),
+                "samples": len(sm), "power_w_max": max(s[1] for s in self.samples)}
 
 
 # ---------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's CPU implementation, all host threads
 # ---------------------------------------------------------------------------------------------------------------
 def cpu_reference_rate(args, steps, warmup, sample_classes):
+    """Times the oracle port of Os2dHead.forward on the host.  The thread count is the best of a short sweep
+    (all hardware threads is rarely the fastest on a 2-socket host); `cores` reports the count actually used."""
     from oracle import head_oracle as ho
-    torch.set_num_threads(os.cpu_count())
     g = torch.Generator().manual_seed(0)
     fm = -(-args.size // 16)
     cms = [(torch.randn(1, D, 15, 15, generator=g) * 0.5 + 0.2).relu() for _ in range(sample_classes)]
     fmap = (torch.randn(args.batch, D, fm, fm, generator=g) * 0.5 + 0.2).relu()
     tn = ho.random_transform_net(6, seed=1, spread=0.005)
     cf = ho.prepare_class_features(cms)
+    ncpu = os.cpu_count() or 1
+
+    def run_once():
+        ho.head_forward(cf, fmap, tn, False, True, class_chunk=sample_classes)
+
+    best_t, best_n = None, ncpu
     with torch.no_grad():
+        for n in sorted(set(x for x in (8, 16, 32, 64, ncpu // 2, ncpu) if 1 <= x <= ncpu)):
+            torch.set_num_threads(n)
+            run_once()
+            t0 = time.perf_counter()
+            run_once()
+            dt = time.perf_counter() - t0
+            if best_t is None or dt < best_t:
+                best_t, best_n = dt, n
+        torch.set_num_threads(best_n)
         for _ in range(warmup):
-            ho.head_forward(cf, fmap, tn, False, True, class_chunk=sample_classes)
+            run_once()
         t0 = time.perf_counter()
         for _ in range(steps):
-            ho.head_forward(cf, fmap, tn, False, True, class_chunk=sample_classes)
+            run_once()
         dt = time.perf_counter() - t0
     rate = args.batch * sample_classes * steps / dt
-    sample = "{} steps x {} classes x batch {} at {}x{} feature map (oracle port of Os2dHead.forward, torch CPU fp32, {} threads)".format(
-        steps, sample_classes, args.batch, fm, fm, torch.get_num_threads())
-    return rate, dt / steps * 1e3, sample
+    sample = ("{} steps x {} classes x batch {} at {}x{} feature map (oracle port of Os2dHead.forward, torch CPU fp32, "
+              "{} threads = best of a sweep up to {} hardware threads)").format(steps, sample_classes, args.batch, fm, fm,
+                                                                              best_n, ncpu)
+    return rate, dt / steps * 1e3, sample, best_n
 
 
 def run_reference(args):
@@ -143,12 +162,12 @@ def run_reference(args):
         return
     sample_classes = max(1, min(args.cpu_sample_classes, args.classes))
     steps = max(1, args.steps)
-    rate, ms, sample = cpu_reference_rate(args, steps, max(1, min(args.warmup, 2)), sample_classes)
+    rate, ms, sample, used = cpu_reference_rate(args, steps, max(1, min(args.warmup, 2)), sample_classes)
     cfg = workload_config(args, args.gpus)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32", "data": "synthetic", "config": cfg,
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -310,8 +329,8 @@ def run_ours(args):
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         sc = max(1, min(args.cpu_sample_classes, C))
-        rate, _, sample = cpu_reference_rate(args, 3, 1, sc)
-        cpu_baseline = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample}
+        rate, _, sample, used = cpu_reference_rate(args, 3, 1, sc)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": used, "kind": "port", "sample": sample}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
