@@ -98,7 +98,7 @@ class ClockSampler:
             except Exception as e:   # noqa: BLE001
                 self.err = repr(e)
                 break
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def stop(self):
         self.stop_flag = True
@@ -338,7 +338,7 @@ def run_ours(args):
             "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": 7 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+            "gpu_launches": 6 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
     line.update(extra)
     print(json.dumps(line), flush=True)
     if world > 1:

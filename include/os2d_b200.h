@@ -56,11 +56,13 @@ int os2d_correlate(const void* img_packed, const void* cls_packed, int B, int C,
                    void* rawvol, void* stream);
 
 /* ---- K2: TransformNet convolution layers (head.py:604-655) -------------------------------------------
- * layer 1: 225(+DC)->128 k7, BN+ReLU; layer 2: 128->64 k5 (hi/lo weight rows), BN+ReLU; layer 3: 64->P k5.
- * wblob: weights packed by os2d_b200.head.pack_transform_net (shared-memory image, see csrc/conv.cu);
- * alpha/beta: 128 floats each (folded BN scale/shift incl. operand pre-scales).
- * in/out volumes: fp16 [planes, chunks8, H*W, 8]; layer 3 writes fp32 [planes, P, H*W]. */
+ * layer 1: 225(+DC)->128 k7, BN+ReLU -> h1 [planes,16,H*W,8] fp16;
+ * layer 2: 128->64 k5 (hi/lo weight rows), BN+ReLU -> h2 [planes,16,H*W,8] fp16 (chunks 0..7 value, 8..15 residual);
+ * layer 3: 64->P k5 in scatter form (csrc/conv3s.cu) -> fp32 [planes, P, H*W]; alpha[0] = 1/weight scale, beta = bias.
+ * wblob: weights packed by os2d_b200.head.pack_transform_net (shared-memory images, see csrc/conv.cu, conv3s.cu);
+ * alpha/beta: 128 floats each (folded BN scale/shift incl. operand pre-scales). */
 size_t os2d_conv_weight_blob_bytes(int ksize, int in_chunks16);
+size_t os2d_conv3_weight_blob_bytes(int P);
 int os2d_transform_conv(int layer, int out_real, const void* in_vol, const void* wblob, const float* alpha,
                         const float* beta, void* out, int planes, int H, int W, void* stream);
 

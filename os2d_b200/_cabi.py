@@ -25,6 +25,7 @@ SIGNATURES = {
     "os2d_correlate": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
                                 _c_void_p]),
     "os2d_conv_weight_blob_bytes": (ctypes.c_size_t, [_c_int, _c_int]),
+    "os2d_conv3_weight_blob_bytes": (ctypes.c_size_t, [_c_int]),
     "os2d_transform_conv": (_c_int, [_c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
                                      _c_int, _c_int, _c_void_p]),
     "os2d_resample_boxes": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float,

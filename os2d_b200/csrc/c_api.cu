@@ -97,6 +97,7 @@ int os2d_correlate(const void* img_packed, const void* cls_packed, int B, int C,
 }
 
 size_t os2d_conv_weight_blob_bytes(int ksize, int in_chunks16) { return conv_weight_blob_bytes(ksize, in_chunks16); }
+size_t os2d_conv3_weight_blob_bytes(int P) { return conv3s_weight_blob_bytes(P); }
 
 int os2d_transform_conv(int layer, int out_real, const void* in_vol, const void* wblob, const float* alpha,
                         const float* beta, void* out, int planes, int H, int W, void* stream) {
@@ -107,9 +108,11 @@ int os2d_transform_conv(int layer, int out_real, const void* in_vol, const void*
   L.lo_scale = 1.0f / 2048.0f;
   if (layer == 1) { L.ksize = 7; L.in_chunks16 = kCorrPad / 16; L.out_real = 128; L.mode = 0; }
   else if (layer == 2) { L.ksize = 5; L.in_chunks16 = 8; L.out_real = 64; L.mode = 1; }
-  else if (layer == 3) { L.ksize = 5; L.in_chunks16 = 4; L.out_real = out_real; L.mode = 2; }
-  else return kErrBadArg;
-  if (layer == 3 && (out_real < 1 || out_real > 64)) return kErrBadArg;
+  else if (layer == 3) {
+    // scatter-form kernel: wblob = conv3s blob, alpha[0] = 1 / weight scale, beta[0..P) = bias
+    return launch_conv3s(in_vol, wblob, beta, alpha, reinterpret_cast<float*>(out), planes, out_real, H, W, sms,
+                         static_cast<cudaStream_t>(stream));
+  } else return kErrBadArg;
   return launch_conv(L, in_vol, wblob, alpha, beta, out, planes, H, W, sms, static_cast<cudaStream_t>(stream));
 }
 

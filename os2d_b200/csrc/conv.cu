@@ -13,20 +13,22 @@
 //   * a CTA tile = 2 strips (8 px wide, up to 32 rows) => two N<=256 accumulators = all 512 TMEM columns;
 //     every weight byte fetched from L2 is used for 512 pixels.
 // Epilogue modes: see ConvLayerDesc in kernels.h (BN folded to fp32 alpha/beta, hi/lo weight rows combined).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace os2d {
 namespace conv {
 
-constexpr int THREADS = 256;
+constexpr int THREADS = 128 + 256;   // 4 control warps + 8 epilogue warps (one group of 4 per strip)
 constexpr int NUM_H = 2;   // halo ring depth
 constexpr int NUM_W = 4;   // weight ring depth
 constexpr uint32_t TAP_BYTES = 2 * 128 * 16;   // one tap, 16 input channels: [2][128 rows][16 B]
 constexpr uint32_t TRANS_STRIDE = 32 * 16 + 16;  // per-warp transpose staging: chunk stride (bank skew)
 constexpr uint32_t TRANS_BYTES = 4 * TRANS_STRIDE;  // per warp
 constexpr uint32_t COMB_STRIDE = 33;                // floats per row in the hi/lo combine staging
-constexpr uint32_t COMB_BYTES = 64 * COMB_STRIDE * 4;
+constexpr uint32_t COMB_BYTES = 2 * 64 * COMB_STRIDE * 4;   // one buffer per strip group
 
 template <int KS>
 struct Geo {
@@ -35,7 +37,7 @@ struct Geo {
   static constexpr int HWY = kMaxTileRows + 2 * PAD;               // halo rows (box height)
   static constexpr uint32_t HALO_BYTES = 2u * HWY * HWX * 16u;
   static constexpr uint32_t WSTAGE_BYTES = KS * TAP_BYTES;
-  static constexpr uint32_t SMEM_BYTES = NUM_H * HALO_BYTES + NUM_W * WSTAGE_BYTES + 4 * TRANS_BYTES + COMB_BYTES +
+  static constexpr uint32_t SMEM_BYTES = NUM_H * HALO_BYTES + NUM_W * WSTAGE_BYTES + 8 * TRANS_BYTES + COMB_BYTES +
                                          256 /*barriers*/ + 128 /*align*/;
 };
 
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
   uint8_t* halo = smem;
   uint8_t* wst = halo + NUM_H * G::HALO_BYTES;
   uint8_t* trans = wst + NUM_W * G::WSTAGE_BYTES;
-  float* comb = reinterpret_cast<float*>(trans + 4 * TRANS_BYTES);
+  float* comb = reinterpret_cast<float*>(trans + 8 * TRANS_BYTES);
   uint64_t* hfull = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(comb) + COMB_BYTES);
   uint64_t* hempty = hfull + NUM_H;
   uint64_t* wfull = hempty + NUM_H;
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
     for (int i = 0; i < NUM_H; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1); }
     for (int i = 0; i < NUM_W; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
     mbar_init(tfull, 1);
-    mbar_init(tempty, 4);
+    mbar_init(tempty, 8);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -164,14 +166,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
-    const int e = warp - 4;
+    // 8 warps: e = TMEM lane quadrant (warp % 4), sg = strip group; each group of 4 warps drains one strip's accumulator
+    const int e = warp & 3, sg = (warp - 4) >> 2;
     const int row = e * 32 + lane;                 // accumulator row = output channel (or hi/lo row)
-    uint8_t* my_trans = trans + e * TRANS_BYTES;
+    uint8_t* my_trans = trans + (warp - 4) * TRANS_BYTES;
+    float* my_comb = comb + sg * (64 * COMB_STRIDE);
     float alpha = 0.f, beta = 0.f;
     if (P.mode == 0 || row < 64) { alpha = P.alpha[row]; beta = P.beta[row]; }
     uint32_t tph = 0;
     const size_t HW = static_cast<size_t>(P.H) * P.W;
-    const int out_chunks = (P.mode == 0) ? 16 : 8;
+    const int out_chunks = 16;   // conv1: 128 channels; conv2: 64 hi + 64 residual
     for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
       const int plane = t / tiles_per_plane;
       const int rem = t - plane * tiles_per_plane;
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
 
       mbar_wait(tfull, tph);
       tc_fence_after();
-      for (int s = 0; s < nstrips; ++s) {
+      for (int s = sg; s < nstrips; s += 2) {
         for (int rq = 0; rq < nquads; ++rq) {
           uint32_t r[32];
           tmem_ld32(tmem_base + s * 256 + rq * 32 + (static_cast<uint32_t>(e * 32) << 16), r);
@@ -195,50 +199,48 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
           if (P.mode != 0) {
             // combine hi rows (0..63) with lo rows (64..127): lo warps publish, hi warps consume
             if (e >= 2) {
-              float* dst = comb + (row - 64) * COMB_STRIDE;
+              float* dst = my_comb + (row - 64) * COMB_STRIDE;
 #pragma unroll
               for (int j = 0; j < 32; ++j) dst[j] = v[j];
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + sg) : "memory");
             if (e < 2) {
-              const float* src = comb + row * COMB_STRIDE;
+              const float* src = my_comb + row * COMB_STRIDE;
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaf(src[j], P.lo_scale, v[j]);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + sg) : "memory");
           }
 
           // pixel j of this block: image row y0 + 4*rq + j/8, column x0 + 8*s + j%8
-          if (P.mode == 2) {
-            if (row < P.out_real) {
-              float* o = reinterpret_cast<float*>(P.out) + (static_cast<size_t>(plane) * P.out_real + row) * HW;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int y = y0 + 4 * rq + (j >> 3), x = x0 + kStripW * s + (j & 7);
-                if (y < P.H && (4 * rq + (j >> 3)) < rows && x < P.W) o[static_cast<size_t>(y) * P.W + x] = fmaf(alpha, v[j], beta);
-              }
-            }
-          } else if (P.mode == 0 || e < 2) {
-            // BN + ReLU -> fp16, transpose 32 channels x 32 pixels through shared memory
+          if (P.mode == 0 || e < 2) {
+            // BN + ReLU -> fp16 (mode 1: fp16 hi plane + fp16 residual plane, consumed by the scatter-form conv3),
+            // transpose 32 channels x 32 pixels through shared memory
             const uint32_t cl = lane >> 3, pos = lane & 7;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const __half hv = __float2half(fmaxf(fmaf(alpha, v[j], beta), 0.f));
-              *reinterpret_cast<__half*>(my_trans + cl * TRANS_STRIDE + j * 16 + pos * 2) = hv;
-            }
-            __syncwarp();
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(alpha, v[j], beta), 0.f);
             const int y = y0 + 4 * rq + (lane >> 3), x = x0 + kStripW * s + (lane & 7);
             const bool ok = (4 * rq + (lane >> 3)) < rows && x < P.W;
+            const int npass = (P.mode == 1) ? 2 : 1;
+            for (int pass = 0; pass < npass; ++pass) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 val = *reinterpret_cast<const uint4*>(my_trans + q * TRANS_STRIDE + lane * 16);
-              if (ok) {
-                __half* o = reinterpret_cast<__half*>(P.out) +
-                            ((static_cast<size_t>(plane) * out_chunks + (e * 4 + q)) * HW + static_cast<size_t>(y) * P.W + x) * 8;
-                *reinterpret_cast<uint4*>(o) = val;
+              for (int j = 0; j < 32; ++j) {
+                const __half hi = __float2half(v[j]);
+                const __half hv = (pass == 0) ? hi : __float2half(v[j] - __half2float(hi));
+                *reinterpret_cast<__half*>(my_trans + cl * TRANS_STRIDE + j * 16 + pos * 2) = hv;
               }
+              __syncwarp();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 val = *reinterpret_cast<const uint4*>(my_trans + q * TRANS_STRIDE + lane * 16);
+                if (ok) {
+                  __half* o = reinterpret_cast<__half*>(P.out) +
+                              ((static_cast<size_t>(plane) * out_chunks + (pass * 8 + e * 4 + q)) * HW + static_cast<size_t>(y) * P.W + x) * 8;
+                  *reinterpret_cast<uint4*>(o) = val;
+                }
+              }
+              __syncwarp();
             }
-            __syncwarp();
           }
         }
       }
@@ -272,12 +274,19 @@ static int launch_t(const ConvLayerDesc& L, const void* in_vol, const void* wblo
   }
   Params P;
   P.planes = planes; P.H = H; P.W = W;
+  P.TXP = (W + kStripW * kStripsPerTile - 1) / (kStripW * kStripsPerTile);
+  // Tile height: the fewest row tiles that fit 32 rows, split evenly (even T).  Measured on B200 at 80x80, C = 100:
+  // T = 28 (3 row tiles) 1.24 ms vs T = 20..24 (4 row tiles, better wave balance on paper) 1.41 ms - taller tiles win
+  // because the per-tile epilogue is not overlapped and N >= 224 keeps the MMA shared-memory read rate low.
   const int nty = (H + kMaxTileRows - 1) / kMaxTileRows;
   int T = (H + nty - 1) / nty;
   T = (T + 1) & ~1;
+  if (const char* ev = getenv("OS2D_B200_CONV_TILE_ROWS")) {   // tuning override (even, 2..32)
+    const int v = atoi(ev);
+    if (v >= 2 && v <= kMaxTileRows && (v & 1) == 0) T = v;
+  }
   P.T = T;
   P.TY = (H + T - 1) / T;
-  P.TXP = (W + kStripW * kStripsPerTile - 1) / (kStripW * kStripsPerTile);
   P.total_tiles = planes * P.TY * P.TXP;
   P.nsub = L.in_chunks16;
   P.mode = L.mode;
@@ -306,7 +315,7 @@ size_t conv_weight_blob_bytes(int ksize, int in_chunks16) {
 
 int launch_conv(const ConvLayerDesc& L, const void* in_vol, const void* wblob, const float* alpha, const float* beta,
                 void* out, int planes, int H, int W, int num_sms, cudaStream_t st) {
-  if (planes <= 0 || H <= 0 || W <= 0 || L.in_chunks16 <= 0 || L.mode < 0 || L.mode > 2) return kErrBadArg;
+  if (planes <= 0 || H <= 0 || W <= 0 || L.in_chunks16 <= 0 || L.mode < 0 || L.mode > 1) return kErrBadArg;
   if ((static_cast<uint64_t>(16) * W) % 16 != 0) return kErrBadArg;
   if (L.ksize == 7) return conv::launch_t<7>(L, in_vol, wblob, alpha, beta, out, planes, H, W, num_sms, st);
   if (L.ksize == 5) return conv::launch_t<5>(L, in_vol, wblob, alpha, beta, out, planes, H, W, num_sms, st);

@@ -6,7 +6,8 @@
 // One CTA tile = 128 image locations (MMA M, one TMEM lane per location) x one class's 240 padded
 // correlation channels (MMA N), K = D in 64-element TMA boxes (128B swizzle) through a 4-stage
 // mbarrier ring.  Warp roles: 0 = TMA producer, 1 = MMA issuer (one thread), 2 = TMEM allocator,
-// 4..7 = epilogue (one thread per location => the 225-channel reductions are thread-local).
+// 4..19 = epilogue: 4 lane quadrants x 4 column groups; a thread owns one location and 64 channels, the
+// 225-channel sums are combined over the 4 column groups through shared memory (one named barrier per tile).
 // The accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of tile t overlaps
 // the MMAs of tile t+1.
 //
@@ -24,8 +25,8 @@ constexpr int BM = 128, BN = kCorrPad, BK = 64, STAGES = 4;
 constexpr uint32_t A_BYTES = BM * BK * 2;          // 16384
 constexpr uint32_t B_BYTES = BN * BK * 2;          // 30720
 constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;  // 47104 = 46 * 1024
-constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int THREADS = 256;
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * 4 * 128 * 8 /*partial sums*/;
+constexpr int THREADS = 128 + 512;   // 4 control warps + 16 epilogue warps
 constexpr uint32_t TMEM_COLS = 512, ACC_COLS = 256;
 
 struct Params {
@@ -44,6 +45,7 @@ corr_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float2* part = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 256);   // [2 acc stages][4 col groups][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = P.D / BK;
@@ -54,7 +56,7 @@ corr_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -113,22 +115,27 @@ corr_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------ epilogue ------------------------------
-    const int e = warp - 4;
+    // ------------------------------ epilogue (16 warps) ------------------------------
+    // warp -> TMEM lane quadrant q = warp % 4 (hardware restriction) and column group cg = (warp - 4) / 4:
+    // columns [64 cg, 64 cg + 64) (the last group holds 48: channels 192..224, the DC side channels and padding).
+    const int q = warp & 3, cg = (warp - 4) >> 2;
+    const int ncb = (cg == 3) ? 3 : 4;                      // 16-column blocks owned by this warp
     int as = 0; uint32_t aphase = 0;
     const float inv_n = 1.0f / static_cast<float>(kCorrCh);
+    const float corr_scale = 1.0f / (kScaleFeat * kScaleFeat);
     for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
       const int plane = t / P.MT, mt = t - plane * P.MT;
-      const int pix = mt * BM + e * 32 + lane;
+      const int row = q * 32 + lane;
+      const int pix = mt * BM + row;
       const bool valid = pix < P.N;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const uint32_t tbase = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(e * 32) << 16);
+      const uint32_t tbase = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + cg * 64;
 
-      // pass 1: thread-local sums over the 225 channels (accumulator = 1024 * corr)
+      // pass 1: partial sums over this warp's columns (accumulator = 1024 * corr), exchanged through shared memory
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-      for (int cb = 0; cb < BN / 16; ++cb) {
+      for (int cb = 0; cb < ncb; ++cb) {
         uint32_t r[16];
         tmem_ld16(tbase + cb * 16, r);
         tmem_ld_wait();
@@ -139,36 +146,52 @@ corr_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__
           s2 = fmaf(v, v, s2);
         }
       }
+      float2* pbuf = part + as * (4 * BM);
+      pbuf[cg * BM + row] = make_float2(s1, s2);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+      s1 = 0.f; s2 = 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) { const float2 v = pbuf[g * BM + row]; s1 += v.x; s2 += v.y; }
+
       // z_k = relu(acc_k) / (sqrt(s2) + 1024 * 1e-6)
       const float inv = 1.0f / (sqrtf(s2) + (kScaleFeat * kScaleFeat) * 1e-6f);
       const float mean = s1 * inv * inv_n;
-      const float m8 = mean * kScaleMean;
-      const __half mh = __float2half(m8);
-      const __half ml = __float2half(m8 - __half2float(mh));
-      const float corr_scale = 1.0f / (kScaleFeat * kScaleFeat);
+      const float zs = inv * kScaleZ, zo = -mean * kScaleZ;
 
-      __half* zbase = P.zvol + (static_cast<size_t>(plane) * kZChunks * P.N + pix) * 8;
-      __half* rbase = P.rawvol + static_cast<size_t>(plane) * kCorrCh * P.N + pix;
-      // pass 2: write z (centred, fp16, chunk8 layout) and raw correlation (fp16, channel-major)
+      __half* zbase = P.zvol + ((static_cast<size_t>(plane) * kZChunks + cg * 8) * P.N + pix) * 8;
+      __half* rptr = P.rawvol + (static_cast<size_t>(plane) * kCorrCh + cg * 64) * P.N + pix;
+      // pass 2: z (centred, fp16, chunk8 layout) and raw correlation (fp16, channel-major)
 #pragma unroll 1
-      for (int cb = 0; cb < BN / 16; ++cb) {
+      for (int cb = 0; cb < ncb; ++cb) {
         uint32_t r[16];
         tmem_ld16(tbase + cb * 16, r);
         tmem_ld_wait();
-        __align__(16) __half hz[16];
+        uint32_t zq[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int k = cb * 16 + j;
-          const float a = __uint_as_float(r[j]);
-          float zc = (fmaxf(a, 0.f) * inv - mean) * kScaleZ;
-          __half hv = __float2half(zc);
-          if (k >= kCorrCh) hv = (k == kDcCh || k == kDcCh + 1) ? mh : ((k == kDcCh + 2) ? ml : __float2half(0.f));
-          hz[j] = hv;
-          if (valid && k < kCorrCh) rbase[static_cast<size_t>(k) * P.N] = __float2half(a * corr_scale);
+        for (int j = 0; j < 16; j += 2) {
+          const float a0 = __uint_as_float(r[j]), a1 = __uint_as_float(r[j + 1]);
+          const __half2 hz = __floats2half2_rn(fmaf(fmaxf(a0, 0.f), zs, zo), fmaf(fmaxf(a1, 0.f), zs, zo));
+          zq[j >> 1] = *reinterpret_cast<const uint32_t*>(&hz);
+          const __half2 hr = __floats2half2_rn(a0 * corr_scale, a1 * corr_scale);
+          const int k = cg * 64 + cb * 16 + j;
+          if (valid && k < kCorrCh) rptr[0] = __low2half(hr);
+          if (valid && k + 1 < kCorrCh) rptr[P.N] = __high2half(hr);
+          rptr += 2 * static_cast<size_t>(P.N);
+        }
+        if (cg == 3 && cb == 2) {
+          // channels 224..239: 224 real, 225/226 = fp16(8 * mean), 227 = residual, 228.. zero
+          const float m8 = mean * kScaleMean;
+          const __half mh = __float2half(m8);
+          const __half ml = __float2half(m8 - __half2float(mh));
+          const __half2 p0 = __halves2half2(__low2half(*reinterpret_cast<const __half2*>(&zq[0])), mh);
+          const __half2 p1 = __halves2half2(mh, ml);
+          zq[0] = *reinterpret_cast<const uint32_t*>(&p0);
+          zq[1] = *reinterpret_cast<const uint32_t*>(&p1);
+          zq[2] = zq[3] = zq[4] = zq[5] = zq[6] = zq[7] = 0u;
         }
         if (valid) {
-          *reinterpret_cast<uint4*>(zbase + static_cast<size_t>(2 * cb) * P.N * 8) = *reinterpret_cast<uint4*>(&hz[0]);
-          *reinterpret_cast<uint4*>(zbase + static_cast<size_t>(2 * cb + 1) * P.N * 8) = *reinterpret_cast<uint4*>(&hz[8]);
+          *reinterpret_cast<uint4*>(zbase + static_cast<size_t>(2 * cb) * P.N * 8) = make_uint4(zq[0], zq[1], zq[2], zq[3]);
+          *reinterpret_cast<uint4*>(zbase + static_cast<size_t>(2 * cb + 1) * P.N * 8) = make_uint4(zq[4], zq[5], zq[6], zq[7]);
         }
       }
       tc_fence_before();

@@ -21,6 +21,7 @@ constexpr float kScaleMean = 8.0f;        // per-pixel mean of z -> fp16 hi/lo p
 constexpr int kStripW = 8;                // a strip is 8 pixels wide
 constexpr int kStripsPerTile = 2;         // two adjacent strips share one halo box
 constexpr int kMaxTileRows = 32;          // 8 * 32 = 256 = max MMA N
+constexpr int kMinTileRows = 20;          // N >= 160 keeps the per-MMA shared-memory read rate under 128 B/clk
 
 int launch_pack_class(const float* maps, int C, int D, int h, int w, int normalize, float* cf32, void* packed,
                       cudaStream_t st);
@@ -37,7 +38,7 @@ struct ConvLayerDesc {
   int out_real;       // real output channels (128, 64, P)
   int mode;           // 0: relu(alpha*acc+beta) -> fp16 chunk8 volume (128 rows)
                       // 1: combine hi/lo rows (c, c+64), relu(alpha*acc+beta) -> fp16 chunk8 volume (64 ch)
-                      // 2: combine hi/lo rows, alpha*acc+beta -> fp32 planar [plane][out_real][H][W]
+                      //    as two planes sets: chunks 0..7 = fp16 value, chunks 8..15 = fp16 residual
   float lo_scale;     // factor applied to the lo-row accumulator before adding (2^-11) in modes 1/2
 };
 int launch_conv(const ConvLayerDesc& L, const void* in_vol, const void* wblob, const float* alpha, const float* beta,
@@ -62,5 +63,10 @@ int launch_nms(const float* boxes, const int32_t* order, const int32_t* seg_offs
                uint8_t* keep, cudaStream_t st);
 
 size_t conv_weight_blob_bytes(int ksize, int in_chunks16);
+
+// scatter-form last layer (conv3s.cu): h2 volume [planes][16 chunk8][H*W][8] -> params fp32 [planes][P][H*W]
+size_t conv3s_weight_blob_bytes(int P);
+int launch_conv3s(const void* h2_vol, const void* wblob, const float* bias, const float* inv_scale, float* out, int planes,
+                  int P, int H, int W, int num_sms, cudaStream_t st);
 
 }  // namespace os2d

@@ -62,44 +62,52 @@ __global__ void __launch_bounds__(256) pack_class_kernel(const float* __restrict
   }
 }
 
-// per-pixel 32 / (||f|| + 1e-5): thread per pixel, coalesced over pixels.  grid (ceil(N/256), B)
-__global__ void __launch_bounds__(256) image_norm_kernel(const float* __restrict__ fm, int D, int N,
-                                                          float* __restrict__ inv) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
-  if (p >= N) return;
-  const float* src = fm + static_cast<size_t>(b) * D * N + p;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int d = 0;
-  for (; d + 3 < D; d += 4) {
-    float a0 = src[static_cast<size_t>(d) * N], a1 = src[static_cast<size_t>(d + 1) * N];
-    float a2 = src[static_cast<size_t>(d + 2) * N], a3 = src[static_cast<size_t>(d + 3) * N];
-    s0 += a0 * a0; s1 += a1 * a1; s2 += a2 * a2; s3 += a3 * a3;
-  }
-  for (; d < D; ++d) { float a = src[static_cast<size_t>(d) * N]; s0 += a * a; }
-  inv[static_cast<size_t>(b) * N + p] = kScaleFeat / (sqrtf((s0 + s1) + (s2 + s3)) + 1e-5f);
-}
-
-// transpose [B][D][N] fp32 -> [B][N][D] fp16 with the per-pixel scale.  tile 64 ch x 32 px.
-// grid (ceil(N/32), D/64, B), block (32, 8)
-__global__ void __launch_bounds__(256) image_pack_kernel(const float* __restrict__ fm, const float* __restrict__ inv,
-                                                          int D, int N, __half* __restrict__ out) {
+// L2-normalise over D and transpose [B][D][N] fp32 -> [B][N][D] fp16 (x 32), one block per 32 pixels.
+// Phase 1 accumulates the squared norms (coalesced 128 B rows, 8 warps striding the channels); phase 2 re-reads the
+// same 128 KB (L2 hits) in 64-channel tiles, transposes through shared memory and writes 128 B per pixel row.
+// grid (ceil(N/32), B), block 256
+__global__ void __launch_bounds__(256) image_pack_kernel(const float* __restrict__ fm, int D, int N,
+                                                          float* __restrict__ inv_out, __half* __restrict__ out) {
+  __shared__ float red[8][33];
+  __shared__ float invs[32];
   __shared__ float tile[64][33];
-  const int b = blockIdx.z, d0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.y, p0 = blockIdx.x * 32, p = p0 + lane;
   const float* src = fm + static_cast<size_t>(b) * D * N;
-  for (int r = threadIdx.y; r < 64; r += 8) {
-    const int p = p0 + threadIdx.x;
-    tile[r][threadIdx.x] = (p < N) ? src[static_cast<size_t>(d0 + r) * N + p] : 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (p < N) {
+    int d = w;
+    for (; d + 24 < D; d += 32) {
+      const float a0 = src[static_cast<size_t>(d) * N + p], a1 = src[static_cast<size_t>(d + 8) * N + p];
+      const float a2 = src[static_cast<size_t>(d + 16) * N + p], a3 = src[static_cast<size_t>(d + 24) * N + p];
+      s0 = fmaf(a0, a0, s0); s1 = fmaf(a1, a1, s1); s2 = fmaf(a2, a2, s2); s3 = fmaf(a3, a3, s3);
+    }
+    for (; d < D; d += 8) { const float a = src[static_cast<size_t>(d) * N + p]; s0 = fmaf(a, a, s0); }
+  }
+  red[w][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (w == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][lane];
+    const float inv = kScaleFeat / (sqrtf(t) + 1e-5f);
+    invs[lane] = inv;
+    if (p < N) inv_out[static_cast<size_t>(b) * N + p] = inv;
   }
   __syncthreads();
-  // each thread writes 2 consecutive channels (half2); 32 lanes cover 64 channels = 128 B per pixel row
-  for (int pr = threadIdx.y; pr < 32; pr += 8) {
-    const int p = p0 + pr;
-    if (p >= N) continue;
-    const float s = inv[static_cast<size_t>(b) * N + p];
-    const int ch = threadIdx.x * 2;
-    __half2 v = __floats2half2_rn(tile[ch][pr] * s, tile[ch + 1][pr] * s);
-    *reinterpret_cast<__half2*>(out + (static_cast<size_t>(b) * N + p) * D + d0 + ch) = v;
+  for (int d0 = 0; d0 < D; d0 += 64) {
+#pragma unroll
+    for (int r = w; r < 64; r += 8) tile[r][lane] = (p < N) ? src[static_cast<size_t>(d0 + r) * N + p] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int pr = w; pr < 32; pr += 8) {
+      if (p0 + pr < N) {
+        const float sc = invs[pr];
+        const __half2 v = __floats2half2_rn(tile[2 * lane][pr] * sc, tile[2 * lane + 1][pr] * sc);
+        *reinterpret_cast<__half2*>(out + (static_cast<size_t>(b) * N + p0 + pr) * D + d0 + 2 * lane) = v;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -115,10 +123,7 @@ int launch_pack_class(const float* maps, int C, int D, int h, int w, int normali
 
 int launch_pack_image(const float* fm, int B, int D, int N, float* inv_ws, void* packed, cudaStream_t st) {
   if (B <= 0 || D <= 0 || N <= 0 || (D % 64) != 0) return kErrBadArg;
-  image_norm_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(fm, D, N, inv_ws);
-  OS2D_CUDA_TRY(cudaGetLastError());
-  image_pack_kernel<<<dim3((N + 31) / 32, D / 64, B), dim3(32, 8), 0, st>>>(fm, inv_ws, D, N,
-                                                                           reinterpret_cast<__half*>(packed));
+  image_pack_kernel<<<dim3((N + 31) / 32, B), 256, 0, st>>>(fm, D, N, inv_ws, reinterpret_cast<__half*>(packed));
   OS2D_CUDA_TRY(cudaGetLastError());
   return kOk;
 }

@@ -121,7 +121,7 @@ def pack_transform_net(sd, out_dim, device):
              *centred* z, so the per-pixel mean enters through DC side channels 225..227 carrying
              V[co,tap] = sum_ci W1 * s1 * 64 / 8 split into fp16 hi/lo (mean is split hi/lo as well).
     layer 2: rows 0..63 = fp16(W2 * s2), rows 64..127 = fp16 residual * 2048 (combined in the epilogue).
-    layer 3: rows 0..P-1 = fp16(W3 * s3), rows 64..64+P-1 = fp16 residual * 2048.
+    layer 3: scatter-form operand of csrc/conv3s.cu: rows (tap, co), fp16 hi planes + unscaled fp16 residual planes.
     """
     f32 = dict((k, v.detach().to(device="cpu", dtype=torch.float64)) for k, v in sd.items() if v.dtype.is_floating_point)
     eps = 1e-5
@@ -165,14 +165,18 @@ def pack_transform_net(sd, out_dim, device):
     s3 = _pow2_scale(w3)
     w3s = w3 * s3
     w3h = w3s.to(torch.float16).to(torch.float64)
-    wp = torch.zeros(128, 64, 5, 5, dtype=torch.float64)
-    wp[:out_dim] = w3h
-    wp[64:64 + out_dim] = (w3s - w3h) * LO_SCALE
+    w3l = (w3s - w3h).to(torch.float16).to(torch.float64)      # unscaled residual: |w3s| < 1 => abs error <= 2^-25
+    # scatter-form operand (csrc/conv3s.cu): rows n = (dy*5 + dx) * P + co, [16 chunk8 (hi 0..7, lo 8..15)][NPAD][8]
+    npad = (25 * out_dim + 15) // 16 * 16
+    rows = torch.zeros(2, npad, 64, dtype=torch.float64)
+    rows[0, :25 * out_dim] = w3h.permute(2, 3, 0, 1).reshape(25 * out_dim, 64)
+    rows[1, :25 * out_dim] = w3l.permute(2, 3, 0, 1).reshape(25 * out_dim, 64)
+    blob3 = rows.view(2, npad, 8, 8).permute(0, 2, 1, 3).reshape(16, npad, 8)
     a3 = torch.zeros(128, dtype=torch.float64)
     b3 = torch.zeros(128, dtype=torch.float64)
-    a3[:out_dim] = 1.0 / s3
+    a3[:] = 1.0 / s3
     b3[:out_dim] = f32["linear.bias"]
-    out["w3"] = _to_blob(wp.float(), 5).to(device)
+    out["w3"] = blob3.to(torch.float16).contiguous().to(device)
     out["alpha3"] = a3.float().to(device).contiguous()
     out["beta3"] = b3.float().to(device).contiguous()
     return out
@@ -346,7 +350,7 @@ class Os2dHead(nn.Module):
             zvol = torch.empty(planes, Z_CHUNKS, N, 8, dtype=torch.float16, device=dev)
             rawvol = torch.empty(planes, CORR_CH, N, dtype=torch.float16, device=dev)
             h1 = torch.empty(planes, 16, N, 8, dtype=torch.float16, device=dev)
-            h2 = torch.empty(planes, 8, N, 8, dtype=torch.float16, device=dev)
+            h2 = torch.empty(planes, 16, N, 8, dtype=torch.float16, device=dev)
             params = torch.empty(planes, P, N, dtype=torch.float32, device=dev)
             cls = self._class_packed[c0:c0 + cc]
             _cabi.check(self._timed("corr", lib.os2d_correlate, _cabi.ptr(img_packed), _cabi.ptr(cls), B, cc, D, H, W,

@@ -87,13 +87,16 @@ def test_packed_transform_net_reproduces_the_convolutions(P):
     assert float((got - ref).abs().max() / ref.abs().max()) < 1e-6
     # ---- layer 3 ----
     h2 = torch.rand(1, 64, 6, 6, generator=g).double()
-    w = _dequant_layer(pw["w3"], 5, 128, 64).double()
-    acc = F.conv2d(h2, w, None, padding=2)
-    got = (acc[:, :P] + acc[:, 64:64 + P] / bh.LO_SCALE) * pw["alpha3"][:P].double().view(1, -1, 1, 1) \
-        + pw["beta3"][:P].double().view(1, -1, 1, 1)
+    # scatter-form blob [16 chunk8 (hi 0..7, lo 8..15)][NPAD][8]: rows (dy*5+dx)*P + co
+    blob = pw["w3"].double()
+    npad = blob.shape[1]
+    assert npad == (25 * P + 15) // 16 * 16
+    wrows = (blob[:8] + blob[8:]).permute(1, 0, 2).reshape(npad, 64)          # hi + lo, [n, ci]
+    assert float(wrows[25 * P:].abs().max()) == 0.0
+    w = wrows[:25 * P].view(5, 5, P, 64).permute(2, 3, 0, 1)                   # [P,64,5,5]
+    got = F.conv2d(h2, w, None, padding=2) * pw["alpha3"][0].double() + pw["beta3"][:P].double().view(1, -1, 1, 1)
     ref = F.conv2d(h2, tn["linear.weight"].double(), tn["linear.bias"].double(), padding=2)
     assert float((got - ref).abs().max()) < 1e-6
-    assert float(w[P:64].abs().max()) == 0.0 and float(w[64 + P:].abs().max()) == 0.0
 
 
 def test_packed_weights_cache_invalidates_on_change():
