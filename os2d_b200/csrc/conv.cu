@@ -27,8 +27,6 @@ constexpr int NUM_W = 4;   // weight ring depth
 constexpr uint32_t TAP_BYTES = 2 * 128 * 16;   // one tap, 16 input channels: [2][128 rows][16 B]
 constexpr uint32_t TRANS_STRIDE = 32 * 16 + 16;  // per-warp transpose staging: chunk stride (bank skew)
 constexpr uint32_t TRANS_BYTES = 4 * TRANS_STRIDE;  // per warp
-constexpr uint32_t COMB_STRIDE = 33;                // floats per row in the hi/lo combine staging
-constexpr uint32_t COMB_BYTES = 2 * 64 * COMB_STRIDE * 4;   // one buffer per strip group
 
 template <int KS>
 struct Geo {
@@ -37,7 +35,7 @@ struct Geo {
   static constexpr int HWY = kMaxTileRows + 2 * PAD;               // halo rows (box height)
   static constexpr uint32_t HALO_BYTES = 2u * HWY * HWX * 16u;
   static constexpr uint32_t WSTAGE_BYTES = KS * TAP_BYTES;
-  static constexpr uint32_t SMEM_BYTES = NUM_H * HALO_BYTES + NUM_W * WSTAGE_BYTES + 8 * TRANS_BYTES + COMB_BYTES +
+  static constexpr uint32_t SMEM_BYTES = NUM_H * HALO_BYTES + NUM_W * WSTAGE_BYTES + 8 * TRANS_BYTES +
                                          256 /*barriers*/ + 128 /*align*/;
 };
 
@@ -54,7 +52,29 @@ struct Params {
   const float* alpha;
   const float* beta;
   void* out;
+  int n_double;       // tiles [0, n_double) are 2-strip tiles; the rest are the last partial wave split in 1-strip tiles
 };
+
+struct TileInfo { int plane, y0, x0, rows, nstrips; };
+
+// Work list: 2-strip tiles (plane, row tile, strip pair) in order; when the last wave of the persistent grid would be
+// less than half full, its 2-strip tiles are split into 1-strip tiles so that the tail costs half a tile per CTA.
+__device__ __forceinline__ TileInfo decode_tile(const Params& P, int t) {
+  int d, s0, ns;
+  if (t < P.n_double) { d = t; s0 = 0; ns = 2; }
+  else { const int u = t - P.n_double; d = P.n_double + (u >> 1); s0 = u & 1; ns = 1; }
+  const int tiles_per_plane = P.TY * P.TXP;
+  TileInfo ti;
+  ti.plane = d / tiles_per_plane;
+  const int rem = d - ti.plane * tiles_per_plane;
+  const int ty = rem / P.TXP, txp = rem - ty * P.TXP;
+  ti.y0 = ty * P.T;
+  ti.x0 = (kStripsPerTile * txp + s0) * kStripW;
+  ti.rows = min(P.T, P.H - ti.y0);
+  const int strips_left = (P.W - ti.x0 + kStripW - 1) / kStripW;
+  ti.nstrips = max(0, min(ns, strips_left));
+  return ti;
+}
 
 template <int KS>
 __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant__ CUtensorMap map_in, Params P) {
@@ -64,8 +84,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
   uint8_t* halo = smem;
   uint8_t* wst = halo + NUM_H * G::HALO_BYTES;
   uint8_t* trans = wst + NUM_W * G::WSTAGE_BYTES;
-  float* comb = reinterpret_cast<float*>(trans + 8 * TRANS_BYTES);
-  uint64_t* hfull = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(comb) + COMB_BYTES);
+  uint64_t* hfull = reinterpret_cast<uint64_t*>(trans + 8 * TRANS_BYTES);
   uint64_t* hempty = hfull + NUM_H;
   uint64_t* wfull = hempty + NUM_H;
   uint64_t* wempty = wfull + NUM_W;
@@ -99,10 +118,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
       int hs = 0; uint32_t hph = 0;
       int ws = 0; uint32_t wph = 0;
       for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-        const int plane = t / tiles_per_plane;
-        const int rem = t - plane * tiles_per_plane;
-        const int ty = rem / P.TXP, txp = rem - ty * P.TXP;
-        const int y0 = ty * P.T, x0 = txp * (kStripW * kStripsPerTile);
+        const TileInfo ti = decode_tile(P, t);
+        if (ti.nstrips == 0) continue;
+        const int plane = ti.plane, y0 = ti.y0, x0 = ti.x0;
         for (int sc = 0; sc < P.nsub; ++sc) {
           mbar_wait(&hempty[hs], hph ^ 1);
           mbar_expect_tx(&hfull[hs], G::HALO_BYTES);
@@ -125,13 +143,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
       int ws = 0; uint32_t wph = 0;
       uint32_t tph = 0;
       for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-        const int plane = t / tiles_per_plane;
-        const int rem = t - plane * tiles_per_plane;
-        const int ty = rem / P.TXP, txp = rem - ty * P.TXP;
-        const int y0 = ty * P.T, x0 = txp * (kStripW * kStripsPerTile);
-        int rows = min(P.T, P.H - y0);
-        rows = (rows + 1) & ~1;
-        const int nstrips = (x0 + kStripW < P.W) ? 2 : 1;
+        const TileInfo ti = decode_tile(P, t);
+        if (ti.nstrips == 0) continue;
+        const int rows = (ti.rows + 1) & ~1;
+        const int nstrips = ti.nstrips;
         const uint32_t idesc = umma_idesc_f16(128, rows * kStripW);
 
         mbar_wait(tempty, tph ^ 1);   // epilogue has drained the accumulators of the previous tile
@@ -170,19 +185,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
     const int e = warp & 3, sg = (warp - 4) >> 2;
     const int row = e * 32 + lane;                 // accumulator row = output channel (or hi/lo row)
     uint8_t* my_trans = trans + (warp - 4) * TRANS_BYTES;
-    float* my_comb = comb + sg * (64 * COMB_STRIDE);
     float alpha = 0.f, beta = 0.f;
-    if (P.mode == 0 || row < 64) { alpha = P.alpha[row]; beta = P.beta[row]; }
+    alpha = P.alpha[row]; beta = P.beta[row];      // 128 entries, indexed by accumulator row
     uint32_t tph = 0;
     const size_t HW = static_cast<size_t>(P.H) * P.W;
     const int out_chunks = 16;   // conv1: 128 channels; conv2: 64 hi + 64 residual
     for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-      const int plane = t / tiles_per_plane;
-      const int rem = t - plane * tiles_per_plane;
-      const int ty = rem / P.TXP, txp = rem - ty * P.TXP;
-      const int y0 = ty * P.T, x0 = txp * (kStripW * kStripsPerTile);
-      const int rows = min(P.T, P.H - y0);
-      const int nstrips = (x0 + kStripW < P.W) ? 2 : 1;
+      const TileInfo ti = decode_tile(P, t);
+      if (ti.nstrips == 0) continue;
+      const int plane = ti.plane, y0 = ti.y0, x0 = ti.x0, rows = ti.rows, nstrips = ti.nstrips;
       const int nquads = (rows + 3) >> 2;
 
       mbar_wait(tfull, tph);
@@ -196,46 +207,57 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 
-          if (P.mode != 0) {
-            // combine hi rows (0..63) with lo rows (64..127): lo warps publish, hi warps consume
-            if (e >= 2) {
-              float* dst = my_comb + (row - 64) * COMB_STRIDE;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) dst[j] = v[j];
-            }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + sg) : "memory");
-            if (e < 2) {
-              const float* src = my_comb + row * COMB_STRIDE;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaf(src[j], P.lo_scale, v[j]);
-            }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + sg) : "memory");
-          }
-
           // pixel j of this block: image row y0 + 4*rq + j/8, column x0 + 8*s + j%8
-          if (P.mode == 0 || e < 2) {
-            // BN + ReLU -> fp16 (mode 1: fp16 hi plane + fp16 residual plane, consumed by the scatter-form conv3),
-            // transpose 32 channels x 32 pixels through shared memory
+          const int y = y0 + 4 * rq + (lane >> 3), x = x0 + kStripW * s + (lane & 7);
+          const bool ok = (4 * rq + (lane >> 3)) < rows && x < P.W;
+          if (P.mode == 0) {
+            // conv1: BN + ReLU -> fp16, transpose 32 channels x 32 pixels through shared memory
             const uint32_t cl = lane >> 3, pos = lane & 7;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(alpha, v[j], beta), 0.f);
-            const int y = y0 + 4 * rq + (lane >> 3), x = x0 + kStripW * s + (lane & 7);
-            const bool ok = (4 * rq + (lane >> 3)) < rows && x < P.W;
-            const int npass = (P.mode == 1) ? 2 : 1;
-            for (int pass = 0; pass < npass; ++pass) {
+            for (int j = 0; j < 32; ++j) {
+              const __half hv = __float2half(fmaxf(fmaf(alpha, v[j], beta), 0.f));
+              *reinterpret_cast<__half*>(my_trans + cl * TRANS_STRIDE + j * 16 + pos * 2) = hv;
+            }
+            __syncwarp();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const __half hi = __float2half(v[j]);
-                const __half hv = (pass == 0) ? hi : __float2half(v[j] - __half2float(hi));
-                *reinterpret_cast<__half*>(my_trans + cl * TRANS_STRIDE + j * 16 + pos * 2) = hv;
+            for (int q = 0; q < 4; ++q) {
+              const uint4 val = *reinterpret_cast<const uint4*>(my_trans + q * TRANS_STRIDE + lane * 16);
+              if (ok) {
+                __half* o = reinterpret_cast<__half*>(P.out) +
+                            ((static_cast<size_t>(plane) * out_chunks + (e * 4 + q)) * HW + static_cast<size_t>(y) * P.W + x) * 8;
+                *reinterpret_cast<uint4*>(o) = val;
+              }
+            }
+            __syncwarp();
+          } else {
+            // conv2: row 32e + l holds output channel 16e + (l & 15), weight part l >> 4 (0 = fp16 hi, 1 = residual * 2048).
+            // Lanes l and l ^ 16 exchange halves: l < 16 finishes pixels 0..15, l >= 16 pixels 16..31 of its channel.
+            const bool upper = lane >= 16;
+            float w[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float other = __shfl_xor_sync(0xffffffffu, upper ? v[j] : v[j + 16], 16);
+              const float hi = upper ? other : v[j];
+              const float lo = upper ? v[j + 16] : other;
+              w[j] = fmaxf(fmaf(alpha, fmaf(lo, P.lo_scale, hi), beta), 0.f);
+            }
+            // output: fp16 value plane (chunks 0..7) + fp16 residual plane (chunks 8..15), 2 chunk8 per warp
+            const uint32_t cl = (lane & 15) >> 3, pos = lane & 7, pbase = upper ? 16u : 0u;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const __half hi = __float2half(w[j]);
+                const __half hv = (pass == 0) ? hi : __float2half(w[j] - __half2float(hi));
+                *reinterpret_cast<__half*>(my_trans + cl * TRANS_STRIDE + (pbase + j) * 16 + pos * 2) = hv;
               }
               __syncwarp();
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
+              for (int q = 0; q < 2; ++q) {
                 const uint4 val = *reinterpret_cast<const uint4*>(my_trans + q * TRANS_STRIDE + lane * 16);
                 if (ok) {
                   __half* o = reinterpret_cast<__half*>(P.out) +
-                              ((static_cast<size_t>(plane) * out_chunks + (pass * 8 + e * 4 + q)) * HW + static_cast<size_t>(y) * P.W + x) * 8;
+                              ((static_cast<size_t>(plane) * out_chunks + (pass * 8 + e * 2 + q)) * HW + static_cast<size_t>(y) * P.W + x) * 8;
                   *reinterpret_cast<uint4*>(o) = val;
                 }
               }
@@ -287,7 +309,16 @@ static int launch_t(const ConvLayerDesc& L, const void* in_vol, const void* wblo
   }
   P.T = T;
   P.TY = (H + T - 1) / T;
-  P.total_tiles = planes * P.TY * P.TXP;
+  {
+    const int doubles = planes * P.TY * P.TXP;
+    const int grid_sz = doubles < num_sms ? doubles : num_sms;
+    const int rem = doubles % grid_sz;
+    // split the last wave into 1-strip tiles when that halves its cost (it does iff 2 * rem <= grid)
+    const bool split = rem > 0 && 2 * rem <= grid_sz;
+    P.n_double = split ? doubles - rem : doubles;
+    P.total_tiles = split ? doubles + rem : doubles;
+    if (getenv("OS2D_B200_CONV_NO_TAIL_SPLIT")) { P.n_double = doubles; P.total_tiles = doubles; }
+  }
   P.nsub = L.in_chunks16;
   P.mode = L.mode;
   P.out_real = L.out_real;

@@ -152,14 +152,25 @@ def pack_transform_net(sd, out_dim, device):
     s2 = _pow2_scale(w2)
     w2s = w2 * s2
     w2h = w2s.to(torch.float16).to(torch.float64)
+    # accumulator row of (output channel c, part p): 32 * (c // 16) + 16 * p + c % 16, so that the hi and the residual
+    # row of a channel sit in lanes l and l ^ 16 of the same epilogue warp (combined with one shuffle, csrc/conv.cu)
+    cidx = torch.arange(64)
+    row_hi = 32 * (cidx // 16) + (cidx % 16)
+    row_lo = row_hi + 16
     wp = torch.zeros(128, 128, 5, 5, dtype=torch.float64)
-    wp[:64] = w2h
-    wp[64:] = (w2s - w2h) * LO_SCALE
+    wp[row_hi] = w2h
+    wp[row_lo] = (w2s - w2h) * LO_SCALE
     a2, b2 = bn_fold("conv.3", "conv.4")
-    pad = torch.zeros(64, dtype=torch.float64)
+    alpha2 = torch.zeros(128, dtype=torch.float64)
+    beta2 = torch.zeros(128, dtype=torch.float64)
+    alpha2[row_hi] = a2 / s2
+    alpha2[row_lo] = a2 / s2
+    beta2[row_hi] = b2
+    beta2[row_lo] = b2
     out["w2"] = _to_blob(wp.float(), 5).to(device)
-    out["alpha2"] = torch.cat([a2 / s2, pad]).float().to(device).contiguous()
-    out["beta2"] = torch.cat([b2, pad]).float().to(device).contiguous()
+    out["alpha2"] = alpha2.float().to(device).contiguous()
+    out["beta2"] = beta2.float().to(device).contiguous()
+    out["row_hi2"] = row_hi
     # ---- layer 3 ----
     w3 = f32["linear.weight"]                      # [P,64,5,5]
     s3 = _pow2_scale(w3)

@@ -78,8 +78,10 @@ def test_packed_transform_net_reproduces_the_convolutions(P):
     h1 = torch.rand(1, 128, 7, 9, generator=g).double()
     w = _dequant_layer(pw["w2"], 5, 128, 128).double()
     acc = F.conv2d(h1, w, None, padding=2)
-    comb = acc[:, :64] + acc[:, 64:] / bh.LO_SCALE
-    got = F.relu(comb * pw["alpha2"][:64].double().view(1, -1, 1, 1) + pw["beta2"][:64].double().view(1, -1, 1, 1))
+    rh = pw["row_hi2"]                                  # hi row of channel c; the residual row is rh + 16
+    comb = acc[:, rh] + acc[:, rh + 16] / bh.LO_SCALE
+    assert torch.equal(pw["alpha2"][rh], pw["alpha2"][rh + 16])
+    got = F.relu(comb * pw["alpha2"][rh].double().view(1, -1, 1, 1) + pw["beta2"][rh].double().view(1, -1, 1, 1))
     a2, b2 = ho.fold_bn(tn["conv.3.weight"], tn["conv.3.bias"], tn["conv.4.weight"], tn["conv.4.bias"],
                         tn["conv.4.running_mean"], tn["conv.4.running_var"])
     ref = F.relu(F.conv2d(h1, tn["conv.3.weight"].double(), None, padding=2) * a2.double().view(1, -1, 1, 1)
