@@ -298,6 +298,32 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    # ---- second figure of the metric: decode + per-class NMS of one image's outputs (all anchors, threshold -inf) ----
+    postproc = None
+    try:
+        from os2d_b200.box_coder import Os2dBoxCoder
+        coder = Os2dBoxCoder(0.5, 0.1, 0.8, 0.4, hc.box_grid_generator_image_level,
+                             lambda s: FeatureMapSize(w=-(-s.w // 16), h=-(-s.h // 16)))
+        with torch.no_grad():
+            loc, score, corners = step(fm_dev)
+        img = FeatureMapSize(w=fm_side * 16, h=fm_side * 16)
+        args_pp = ([loc[0].reshape(C, 4, N)], [score[0].reshape(C, N)], [img], list(range(C)))
+        for _ in range(2):
+            dets = coder.decode_pyramid(*args_pp, nms_score_threshold=float("-inf"), nms_iou_threshold=0.3,
+                                        transform_corners_pyramid=[corners[0].reshape(C, 8, N)])
+        torch.cuda.synchronize()
+        p0 = time.perf_counter()
+        for _ in range(5):
+            dets = coder.decode_pyramid(*args_pp, nms_score_threshold=float("-inf"), nms_iou_threshold=0.3,
+                                        transform_corners_pyramid=[corners[0].reshape(C, 8, N)])
+        torch.cuda.synchronize()
+        pp_ms = (time.perf_counter() - p0) / 5 * 1e3
+        postproc = {"decode_nms_ms_per_image": pp_ms, "candidates": C * N, "detections": len(dets),
+                    "classes_per_s_head_plus_postproc": C / ((ms_total / args.steps + pp_ms) * 1e-3),
+                    "note": "rank-0 classes only, score threshold -inf (every anchor is an NMS candidate)"}
+    except Exception as e:   # noqa: BLE001
+        postproc = {"error": repr(e)}
+
     # ---- roofline of the dominant kernel (conv1 of the TransformNet) + the correlation GEMM ----
     peaks = {}
     try:
@@ -338,7 +364,8 @@ def run_ours(args):
             "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": 6 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+            "gpu_launches": 6 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "postproc": postproc}
     line.update(extra)
     print(json.dumps(line), flush=True)
     if world > 1:

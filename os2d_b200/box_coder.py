@@ -75,6 +75,29 @@ def _segmented_chunked_nms(xyxy, scores, cand, counts, iou_thr):
     lib = _cabi.load()
     dev = xyxy.device
     n_labels = len(counts)
+    if n_labels > 0 and max(counts) <= NMS_MAX_BATCH:
+        # every label is a single chunk: one launch, no per-label host loop.  Segment = label; order inside a segment =
+        # score descending, ties by candidate position (one stable sort on the composite key (label, -score)).
+        total = cand.numel()
+        if total == 0:
+            return cand
+        counts_t = torch.tensor(counts, dtype=torch.int64)
+        seg_off = torch.zeros(n_labels + 1, dtype=torch.int32)
+        seg_off[1:] = counts_t.cumsum(0)
+        seg_id = torch.repeat_interleave(torch.arange(n_labels), counts_t).to(dev)
+        sc = scores[cand]
+        # monotone map float32 -> int64 (larger score => larger value), then key = label * 2^33 - value
+        bits = sc.view(torch.int32).to(torch.int64)
+        mono = torch.where(bits >= 0, bits, (-2 ** 31) - bits - 1)      # negative floats: order reverses with the magnitude bits
+        mono = torch.where(sc == 0, torch.zeros_like(mono), mono)        # -0.0 ties with +0.0
+        key = seg_id * (2 ** 33) - mono
+        perm = torch.sort(key, stable=True)[1]
+        order = cand[perm].to(torch.int32).contiguous()
+        keep = torch.empty(total, dtype=torch.uint8, device=dev)
+        rc = lib.os2d_nms_segments(_cabi.ptr(xyxy), _cabi.ptr(order), _cabi.ptr(seg_off.to(dev)), n_labels,
+                                   float(iou_thr), _cabi.ptr(keep), _cabi.stream_ptr())
+        _cabi.check(rc, "os2d_nms_segments")
+        return cand[perm][keep.bool()]
     active = [True] * n_labels
     result_per_label = [None] * n_labels
     # current survivors per label (tensor of box indices, ordered)
@@ -234,69 +257,95 @@ class Os2dBoxCoder:
             lvl.append((boxes, anchors, cor_out, valid, cls_c, N))
 
         # ---- candidate list in the reference's concatenation order: label (set order), class view, level, anchor ----
+        # Candidates are FLAT indices into the per-level arrays concatenated over levels: f = base_l + c * N_l + n, so that
+        # the NMS kernel reads boxes in place and only the survivors are gathered.
         label_order = list(set(class_ids))                       # same iteration order as box_coder.py:483
         label_rank = {l: r for r, l in enumerate(label_order)}
+        n_labels = len(label_order)
+        ranks_host = [label_rank[c] for c in class_ids]
         L = len(lvl)
-        rank_of_view = torch.tensor([label_rank[c] for c in class_ids], device=device)
-        cand_cls, cand_lvl, cand_n = [], [], []
-        for i_p, (boxes, anchors, cor_out, valid, cls_c, N) in enumerate(lvl):
-            nz = torch.nonzero(valid)                            # sorted by class view, then anchor
-            cand_cls.append(nz[:, 0])
-            cand_n.append(nz[:, 1])
-            cand_lvl.append(torch.full_like(nz[:, 0], i_p))
-        cand_cls = torch.cat(cand_cls)
-        cand_n = torch.cat(cand_n)
-        cand_lvl = torch.cat(cand_lvl)
-        key = (rank_of_view[cand_cls] * num_classes + cand_cls) * L + cand_lvl
-        perm = torch.sort(key, stable=True)[1]
-        cand_cls, cand_n, cand_lvl = cand_cls[perm], cand_n[perm], cand_lvl[perm]
-        M = cand_cls.numel()
+        rank_of_view = torch.tensor(ranks_host, device=device)
+        n_per_level = [t[5] for t in lvl]
+        bases = [0]
+        for nl in n_per_level:
+            bases.append(bases[-1] + num_classes * nl)
+        cat = (lambda xs: xs[0]) if L == 1 else (lambda xs: torch.cat(xs, dim=0))
+        boxes_flat = cat([t[0].view(-1, 4) for t in lvl])
+        scores_flat = cat([t[4].view(-1) for t in lvl])
+        valid_flat = cat([t[3].view(-1) for t in lvl])
+        cand = torch.nonzero(valid_flat).squeeze(1)              # ascending: level, class view, anchor
 
-        # gather candidate boxes / fields
-        all_boxes = torch.empty(M, 4, dtype=torch.float32, device=device)
-        all_scores = torch.empty(M, dtype=torch.float32, device=device)
-        all_anchors = torch.empty(M, 4, dtype=torch.float32, device=device)
-        all_corners = torch.empty(M, 8, dtype=torch.float32, device=device) if have_corners else None
-        for i_p, (boxes, anchors, cor_out, valid, cls_c, N) in enumerate(lvl):
-            m = cand_lvl == i_p
+        def split_index(f):
+            """flat index -> (level, class view, anchor)"""
             if L == 1:
-                m = slice(None)
-            c_i, n_i = cand_cls[m], cand_n[m]
-            all_boxes[m] = boxes[c_i, n_i]
-            all_scores[m] = cls_c[c_i, n_i]
-            all_anchors[m] = anchors[n_i]
-            if have_corners:
-                all_corners[m] = cor_out[c_i, n_i]
-        labels_t = torch.tensor(label_order, dtype=torch.long, device=device)
-        cand_rank = rank_of_view[cand_cls]
-        all_labels = labels_t[cand_rank] if M > 0 else torch.zeros(0, dtype=torch.long, device=device)
+                return torch.zeros_like(f), f // n_per_level[0], f % n_per_level[0]
+            lv = torch.bucketize(f, torch.tensor(bases[1:-1], device=device), right=True)
+            base_t = torch.tensor(bases[:-1], device=device)[lv]
+            nl_t = torch.tensor(n_per_level, device=device)[lv]
+            return lv, (f - base_t) // nl_t, (f - base_t) % nl_t
 
-        if M == 0:
-            # the reference would fail in cat_boxlist([]) (box_coder.py:534); return an empty list instead
-            out = BoxList(all_boxes, out_size if out_size is not None else img_size_pyramid[0])
+        c_lvl, c_cls, c_n = split_index(cand)
+        c_rank = rank_of_view[c_cls]
+        if L > 1 or any(ranks_host[i] > ranks_host[i + 1] for i in range(len(ranks_host) - 1)):
+            key = (c_rank * num_classes + c_cls) * L + c_lvl
+            perm = torch.sort(key, stable=True)[1]
+            cand, c_rank = cand[perm], c_rank[perm]
+
+        # static bound: candidates of a label <= (#views of the label) * (anchors of all levels)
+        views_per_label = max(ranks_host.count(r) for r in set(ranks_host))
+        if views_per_label * sum(n_per_level) <= NMS_MAX_BATCH:
+            # every label is one NMS chunk: stays on the device (no host synchronisation), survivors leave the kernel
+            # grouped by label in set order and score-descending, which is the reference's output order
+            keep = _single_chunk_nms_device(boxes_flat, scores_flat, cand, c_rank, n_labels, nms_iou_threshold)
         else:
-            counts = torch.bincount(cand_rank, minlength=len(label_order)).tolist()
-            counts = [c for c in counts if c > 0]
-            cand = torch.arange(M, device=device)
-            keep = _segmented_chunked_nms(all_boxes, all_scores, cand, counts, nms_iou_threshold)
-            # per label: sort survivors by score, descending (box_coder.py:431-435); labels stay in set order
-            k_rank = cand_rank[keep]
-            k_sc = all_scores[keep]
-            o1 = torch.sort(k_sc, descending=True, stable=True)[1]
-            o2 = torch.sort(k_rank[o1], stable=True)[1]
-            keep = keep[o1[o2]]
-            out = BoxList(all_boxes[keep], out_size)
-            all_scores, all_labels, all_anchors = all_scores[keep], all_labels[keep], all_anchors[keep]
-            if have_corners:
-                all_corners = all_corners[keep]
-        out.add_field("scores", all_scores)
-        out.add_field("default_boxes", BoxList(all_anchors, out.image_size))
-        out.add_field("labels", all_labels)
+            counts = [c for c in torch.bincount(c_rank, minlength=n_labels).tolist() if c > 0]
+            keep = _segmented_chunked_nms(boxes_flat, scores_flat, cand, counts, nms_iou_threshold)
+            if counts and max(counts) > NMS_MAX_BATCH:
+                # chunked path: per label, sort the survivors by score, descending (box_coder.py:431-435)
+                k_rank = rank_of_view[split_index(keep)[1]]
+                o1 = torch.sort(scores_flat[keep], descending=True, stable=True)[1]
+                o2 = torch.sort(k_rank[o1], stable=True)[1]
+                keep = keep[o1[o2]]
+
+        k_lvl, k_cls, k_n = split_index(keep)
+        out = BoxList(boxes_flat[keep], out_size if out_size is not None else img_size_pyramid[0])
+        out.add_field("scores", scores_flat[keep])
+        labels_t = torch.tensor(label_order, dtype=torch.long, device=device)
+        anchors_all = cat([t[1] for t in lvl])                   # [sum N_l, 4]
+        anchor_base = torch.tensor([sum(n_per_level[:i]) for i in range(L)], device=device)
+        out.add_field("default_boxes", BoxList(anchors_all[anchor_base[k_lvl] + k_n], out.image_size))
+        out.add_field("labels", labels_t[rank_of_view[k_cls]] if keep.numel() > 0 else torch.zeros(0, dtype=torch.long, device=device))
         if have_corners:
-            out.add_field("transform_corners", all_corners)
+            out.add_field("transform_corners", cat([t[2].view(-1, 8) for t in lvl])[keep])
         if self.do_nms_across_classes and len(out) > 0:
             out = self._nms_box_lists([out], nms_iou_threshold)
         return out
+
+
+def _single_chunk_nms_device(xyxy, scores, cand, seg_of_cand, n_segs, iou_thr):
+    """Greedy NMS of every segment (each known to hold <= 10000 candidates) in ONE launch without touching the host:
+    segment offsets come from a device-side bincount/cumsum; order inside a segment = score descending, ties by candidate
+    position (one stable sort on the composite key (segment, -score)).  Returns the surviving candidate ids grouped by
+    segment, score-descending."""
+    lib = _cabi.load()
+    dev = xyxy.device
+    total = cand.numel()
+    if total == 0:
+        return cand
+    seg_off = torch.zeros(n_segs + 1, dtype=torch.int32, device=dev)
+    seg_off[1:] = torch.bincount(seg_of_cand, minlength=n_segs).cumsum(0)
+    sc = scores[cand]
+    bits = sc.view(torch.int32).to(torch.int64)
+    mono = torch.where(bits >= 0, bits, (-2 ** 31) - bits - 1)      # monotone float32 -> int64 map
+    mono = torch.where(sc == 0, torch.zeros_like(mono), mono)        # -0.0 ties with +0.0
+    perm = torch.sort(seg_of_cand * (2 ** 33) - mono, stable=True)[1]
+    ordered = cand[perm]
+    order32 = ordered.to(torch.int32)
+    keep = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+    rc = lib.os2d_nms_segments(_cabi.ptr(xyxy), _cabi.ptr(order32), _cabi.ptr(seg_off), n_segs, float(iou_thr),
+                               _cabi.ptr(keep), _cabi.stream_ptr())
+    _cabi.check(rc, "os2d_nms_segments")
+    return ordered[keep[:total].bool()]
 
 
 class _Resize:

@@ -77,8 +77,23 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const float4* __res
     supp[i] = 0;
   }
   __syncthreads();
-  for (int i = 0; i < n; ++i) {
-    if (supp[i]) continue;                       // uniform: everyone reads the same byte after the last barrier
+  __shared__ int s_next;
+  int start = 0;
+  while (true) {
+    // warp 0 finds the next box that is still alive (32 flags per step), everybody else waits at the barrier
+    if (threadIdx.x < 32) {
+      int found = -1;
+      for (int j = start; j < n; j += 32) {
+        const bool alive = (j + static_cast<int>(threadIdx.x) < n) && !supp[j + threadIdx.x];
+        const unsigned m = __ballot_sync(0xffffffffu, alive);
+        if (m) { found = j + __ffs(m) - 1; break; }
+      }
+      if (threadIdx.x == 0) s_next = found;
+    }
+    __syncthreads();
+    const int i = s_next;
+    if (i < 0) break;
+    start = i + 1;
     const float4 bi = sb[i];
     const float iarea = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
     for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {

@@ -47,25 +47,43 @@ __global__ void __launch_bounds__(128) resample_kernel(const __half* __restrict_
   const float cx0 = x + 0.5f, cy0 = y + 0.5f;
   const float xmax = static_cast<float>(W - 1), ymax = static_cast<float>(H - 1);
   float acc = 0.f;
+  const unsigned short* rp16 = reinterpret_cast<const unsigned short*>(rplane);
 #pragma unroll 1
   for (int j = 2; j <= 12; ++j) {          // template x index
     const float xj = lin15(j);
     const float gx_j = fmaf(a, xj, tx), gy_j = fmaf(c, xj, ty);
+    // phase 1: addresses and weights of the 11 points of this template column; phase 2: all 44 taps in flight;
+    // phase 3: interpolate (keeps ~44 independent L2 gathers outstanding per thread instead of 4)
+    int o00[11], ox1[11], oy1[11];
+    float wxs[11], wys[11];
 #pragma unroll
     for (int i = 2; i <= 12; ++i) {        // template y index
       const float yi = lin15(i);
       const float gx = fmaf(b, yi, gx_j), gy = fmaf(d, yi, gy_j);
-      float px = fminf(fmaxf(fmaf(gx, 7.5f, cx0), 0.f), xmax);
-      float py = fminf(fmaxf(fmaf(gy, 7.5f, cy0), 0.f), ymax);
+      const float px = fminf(fmaxf(fmaf(gx, 7.5f, cx0), 0.f), xmax);
+      const float py = fminf(fmaxf(fmaf(gy, 7.5f, cy0), 0.f), ymax);
       const float fx0 = floorf(px), fy0 = floorf(py);
-      const float wx = px - fx0, wy = py - fy0;
+      wxs[i - 2] = px - fx0;
+      wys[i - 2] = py - fy0;
       const int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0);
-      const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-      const __half* ch = rplane + static_cast<size_t>(j * kGrid + i) * N;
-      const float v00 = __half2float(ch[y0 * W + x0]), v01 = __half2float(ch[y0 * W + x1]);
-      const float v10 = __half2float(ch[y1 * W + x0]), v11 = __half2float(ch[y1 * W + x1]);
-      const float top = fmaf(wx, v01 - v00, v00), bot = fmaf(wx, v11 - v10, v10);
-      acc += fmaf(wy, bot - top, top);
+      o00[i - 2] = (j * kGrid + i) * N + y0 * W + x0;
+      ox1[i - 2] = (x0 + 1 < W) ? 1 : 0;
+      oy1[i - 2] = (y0 + 1 < H) ? W : 0;
+    }
+    unsigned short r00[11], r01[11], r10[11], r11[11];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) {
+      r00[i] = __ldg(rp16 + o00[i]);
+      r01[i] = __ldg(rp16 + o00[i] + ox1[i]);
+      r10[i] = __ldg(rp16 + o00[i] + oy1[i]);
+      r11[i] = __ldg(rp16 + o00[i] + oy1[i] + ox1[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 11; ++i) {
+      const float v00 = __half2float(__ushort_as_half(r00[i])), v01 = __half2float(__ushort_as_half(r01[i]));
+      const float v10 = __half2float(__ushort_as_half(r10[i])), v11 = __half2float(__ushort_as_half(r11[i]));
+      const float top = fmaf(wxs[i], v01 - v00, v00), bot = fmaf(wxs[i], v11 - v10, v10);
+      acc += fmaf(wys[i], bot - top, top);
     }
   }
   score[static_cast<size_t>(plane) * score_ps + pix] = acc * (1.0f / 121.0f);
