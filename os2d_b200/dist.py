@@ -37,15 +37,18 @@ def local_views(buffer, rank):
     return blk[:, :, 0:1], blk[:, :, 1:5], blk[:, :, 5:13]
 
 
-def all_gather_outputs(buffer, group=None):
-    """In-place all-gather of every rank's block of ``buffer`` ([world, ...])."""
+def all_gather_outputs(buffer, group=None, async_op=False):
+    """In-place all-gather of every rank's block of ``buffer`` ([world, ...]).  With ``async_op`` the NCCL work handle is
+    returned so that the collective of image i overlaps the kernels of image i+1 (wait before reading / reusing)."""
     world = dist.get_world_size(group)
     if world == 1:
-        return buffer
+        return None if async_op else buffer
     rank = dist.get_rank(group)
-    dist.all_gather_into_tensor(buffer.view(-1), buffer[rank].reshape(-1).clone() if buffer.device.type == "cpu"
-                                else buffer[rank].reshape(-1), group=group)
-    return buffer
+    src = buffer[rank].reshape(-1)
+    if buffer.device.type == "cpu":
+        src = src.clone()          # gloo does not support the in-place form
+    work = dist.all_gather_into_tensor(buffer.view(-1), src, group=group, async_op=async_op)
+    return work if async_op else buffer
 
 
 def unpack_gathered(buffer, num_classes):
@@ -76,12 +79,16 @@ class ClassShardedHead:
         N = H * W
         buf = allocate_gather_buffer(B, self.num_classes, N, self.world, feature_maps.device)
         if self.head is not None:
-            loc, score, _, corners = self.head(feature_maps)
             s_v, l_v, c_v = local_views(buf, self.rank)
             n = self.hi - self.lo
-            s_v[:, :n].copy_(score.reshape(B, n, 1, N))
-            l_v[:, :n].copy_(loc.reshape(B, n, 4, N))
-            c_v[:, :n].copy_(corners.reshape(B, n, 8, N))
+            if getattr(self.head, "supports_out_views", False):
+                # the resample kernel writes straight into this rank's slice of the gather buffer (no staging copy)
+                self.head(feature_maps, out_views=(s_v[:, :n], l_v[:, :n], c_v[:, :n]))
+            else:
+                loc, score, _, corners = self.head(feature_maps)
+                s_v[:, :n].copy_(score.reshape(B, n, 1, N))
+                l_v[:, :n].copy_(loc.reshape(B, n, 4, N))
+                c_v[:, :n].copy_(corners.reshape(B, n, 8, N))
         if self.world > 1:
             all_gather_outputs(buf, self.group)
         loc, score, corners = unpack_gathered(buf, self.num_classes)

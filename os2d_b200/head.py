@@ -12,6 +12,7 @@ Inference only: the kernels implement the eval-mode forward (BatchNorm running s
 Calling the head with gradients required or BatchNorm in training mode raises - there is no PyTorch / CPU
 fallback path in this package.
 """
+import ctypes
 import math
 
 import torch
@@ -306,6 +307,7 @@ class Os2dHead(nn.Module):
         self.class_pool_mask = mask / mask.sum(dim=(2, 3), keepdim=True)     # head.py:295-302
         self.aligner = aligner
         self.max_planes_per_call = 4096
+        self.supports_out_views = True
         # optional per-stage CUDA-event timing (bench.py): list of (stage, start_event, end_event) when not None
         self.profile_events = None
 
@@ -319,9 +321,10 @@ class Os2dHead(nn.Module):
         self.profile_events.append((name, e0, e1))
         return rc
 
-    def forward(self, feature_maps):
+    def forward(self, feature_maps, out_views=None):
         """feature_maps [B,D,H,W] -> (loc [B,C,4,H,W], rec [B,C,1,H,W], rec_transform_detached (same tensor under
-        no-grad, head.py:400-402), corners [B,C,8,H,W])."""
+        no-grad, head.py:400-402), corners [B,C,8,H,W]).  ``out_views`` (extension, default None): (score, loc, corners)
+        strided views [B,C,k,H*W] to write into instead of fresh tensors; the call then returns None."""
         if torch.is_grad_enabled() and (feature_maps.requires_grad or
                                         any(p.requires_grad for p in self.aligner.parameters())):
             raise RuntimeError("os2d_b200.Os2dHead implements inference only; call it under torch.no_grad() "
@@ -349,9 +352,17 @@ class Os2dHead(nn.Module):
         _cabi.check(self._timed("pack_image", lib.os2d_pack_image_features, _cabi.ptr(fm), B, D, N, _cabi.ptr(inv_ws),
                                 _cabi.ptr(img_packed), st), "os2d_pack_image_features")
 
-        loc = torch.empty(B, C, 4, H, W, dtype=torch.float32, device=dev)
-        score = torch.empty(B, C, 1, H, W, dtype=torch.float32, device=dev)
-        corners = torch.empty(B, C, 8, H, W, dtype=torch.float32, device=dev)
+        if out_views is None:
+            loc = torch.empty(B, C, 4, H, W, dtype=torch.float32, device=dev)
+            score = torch.empty(B, C, 1, H, W, dtype=torch.float32, device=dev)
+            corners = torch.empty(B, C, 8, H, W, dtype=torch.float32, device=dev)
+            o_score, o_loc, o_corners = score.view(B, C, 1, N), loc.view(B, C, 4, N), corners.view(B, C, 8, N)
+        else:
+            # caller-owned strided views [B, C, k, N] (inner [k, N] contiguous), e.g. slices of a gather buffer
+            o_score, o_loc, o_corners = out_views
+            for v, k in ((o_score, 1), (o_loc, 4), (o_corners, 8)):
+                assert v.shape == (B, C, k, N) and v.stride(3) == 1 and v.stride(2) == N and v.dtype == torch.float32
+            loc = score = corners = None
 
         # class chunks bound the workspace (z / raw / hidden volumes); classes are independent in eval mode
         cmax = max(1, self.max_planes_per_call // B)
@@ -375,20 +386,21 @@ class Os2dHead(nn.Module):
             _cabi.check(self._timed("conv3", lib.os2d_transform_conv, 3, P, _cabi.ptr(h2), _cabi.ptr(pw["w3"]),
                                     _cabi.ptr(pw["alpha3"]), _cabi.ptr(pw["beta3"]), _cabi.ptr(params), planes, H, W, st),
                         "os2d_transform_conv(3)")
-            if cc == C:
-                o_loc, o_score, o_corners = loc, score, corners
+            # K3 writes straight into the final tensors (or into caller-provided views, e.g. this rank's slice of the
+            # all-gather buffer): one launch when the planes of this chunk are contiguous in the output, else one per image
+            if cc == C and out_views is None:
+                launches = [(0, planes)]
             else:
-                o_loc = torch.empty(B, cc, 4, H, W, dtype=torch.float32, device=dev)
-                o_score = torch.empty(B, cc, 1, H, W, dtype=torch.float32, device=dev)
-                o_corners = torch.empty(B, cc, 8, H, W, dtype=torch.float32, device=dev)
-            _cabi.check(self._timed("resample", lib.os2d_resample_boxes, _cabi.ptr(rawvol), _cabi.ptr(params), planes, P, H,
-                                    W, inverse, float(gen.box_stride.w), float(gen.box_stride.h), float(gen.box_size.w),
-                                    float(gen.box_size.h), _cabi.ptr(o_score), _cabi.ptr(o_loc), _cabi.ptr(o_corners),
-                                    N, 4 * N, 8 * N, st), "os2d_resample_boxes")
-            if cc != C:
-                loc[:, c0:c0 + cc] = o_loc
-                score[:, c0:c0 + cc] = o_score
-                corners[:, c0:c0 + cc] = o_corners
+                launches = [(b, cc) for b in range(B)]
+            for b0, npl in launches:
+                _cabi.check(self._timed("resample", lib.os2d_resample_boxes, _cabi.ptr(rawvol[b0 * cc:]),
+                                        _cabi.ptr(params[b0 * cc:]), npl, P, H, W, inverse, float(gen.box_stride.w),
+                                        float(gen.box_stride.h), float(gen.box_size.w), float(gen.box_size.h),
+                                        ctypes.c_void_p(o_score[b0, c0].data_ptr()), ctypes.c_void_p(o_loc[b0, c0].data_ptr()),
+                                        ctypes.c_void_p(o_corners[b0, c0].data_ptr()), o_score.stride(1), o_loc.stride(1),
+                                        o_corners.stride(1), st), "os2d_resample_boxes")
+        if out_views is not None:
+            return None
         return loc, score, score, corners
 
     @staticmethod
