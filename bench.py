@@ -369,13 +369,25 @@ def run_ours(args):
     flop_conv2 = 2.0 * N * 128 * 64 * 25 * planes
     flop_conv3 = 2.0 * N * 64 * 6 * 25 * planes
 
+    # DRAM traffic per launch from the committed ncu --set full capture (profiles/ncu_traffic.json, cfg-2 sized launch);
+    # only reported when this run has the same launch geometry
+    traffic = {}
+    try:
+        if B == 1 and C == 100 and fm_side == 80:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:   # noqa: BLE001
+        traffic = {}
+    kernel_names = {"conv1": "conv::conv_kernel<7>", "conv2": "conv::conv_kernel<5>", "corr": "corr::corr_kernel"}
+
     def roof(name, flop):
         ms = stage_avg.get(name)
         if not ms:
             return None
         ach = flop / (ms * 1e-3) / 1e12
-        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "ms_per_launch": ms, "peak_source": peak_src}
+        tr = traffic.get(kernel_names.get(name, ""), {}).get("traffic_bytes")
+        return {"kernel": kernel_names.get(name, name), "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": ach / peak_tf, "traffic": tr, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                "algorithmic_flop_per_launch": flop, "ms_per_launch": ms, "peak_source": peak_src}
 
     roofline = roof("conv1", flop_conv1)
     extra = {"roofline_corr": roof("corr", flop_corr), "roofline_conv2": roof("conv2", flop_conv2),
