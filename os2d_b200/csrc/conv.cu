@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
   uint64_t* wfull = hempty + NUM_H;
   uint64_t* wempty = wfull + NUM_W;
   uint64_t* tfull = wempty + NUM_W;
-  uint64_t* tempty = tfull + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+  uint64_t* tempty = tfull + 2;            // one full/empty pair per strip accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -98,8 +98,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NUM_H; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1); }
     for (int i = 0; i < NUM_W; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
-    mbar_init(tfull, 1);
-    mbar_init(tempty, 8);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -112,6 +111,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_plane = P.TY * P.TXP;
 
+  // Strip staggering: with 2 strips the first and the last 16-channel sub-chunk are issued strip by strip (their weight rows
+  // are streamed twice), every other sub-chunk for both strips per weight load.  Strip 0's accumulator is therefore complete
+  // KS*KS MMAs before strip 1's, and each strip has its own TMEM full/empty barrier pair: the epilogue of strip 0 overlaps the
+  // last MMAs of strip 1, and the epilogue of strip 1 overlaps the first MMAs (strip 0) of the next tile.
   if (warp == 0) {
     // ------------------------------ producer: halo boxes (TMA) + weight rows (bulk) ------------------------------
     if (lane == 0) {
@@ -121,17 +124,21 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
         const TileInfo ti = decode_tile(P, t);
         if (ti.nstrips == 0) continue;
         const int plane = ti.plane, y0 = ti.y0, x0 = ti.x0;
+        const bool stag = ti.nstrips == 2 && P.nsub >= 2;
         for (int sc = 0; sc < P.nsub; ++sc) {
           mbar_wait(&hempty[hs], hph ^ 1);
           mbar_expect_tx(&hfull[hs], G::HALO_BYTES);
           tma_load_4d(halo + hs * G::HALO_BYTES, &map_in, &hfull[hs], 8 * (x0 - G::PAD), y0 - G::PAD, 2 * sc, plane);
           if (++hs == NUM_H) { hs = 0; hph ^= 1; }
-          for (int dy = 0; dy < KS; ++dy) {
-            mbar_wait(&wempty[ws], wph ^ 1);
-            mbar_expect_tx(&wfull[ws], G::WSTAGE_BYTES);
-            bulk_load_1d(wst + ws * G::WSTAGE_BYTES, P.wblob + static_cast<size_t>(sc * KS + dy) * G::WSTAGE_BYTES,
-                         G::WSTAGE_BYTES, &wfull[ws]);
-            if (++ws == NUM_W) { ws = 0; wph ^= 1; }
+          const int reps = (stag && (sc == 0 || sc == P.nsub - 1)) ? 2 : 1;
+          for (int rep = 0; rep < reps; ++rep) {
+            for (int dy = 0; dy < KS; ++dy) {
+              mbar_wait(&wempty[ws], wph ^ 1);
+              mbar_expect_tx(&wfull[ws], G::WSTAGE_BYTES);
+              bulk_load_1d(wst + ws * G::WSTAGE_BYTES, P.wblob + static_cast<size_t>(sc * KS + dy) * G::WSTAGE_BYTES,
+                           G::WSTAGE_BYTES, &wfull[ws]);
+              if (++ws == NUM_W) { ws = 0; wph ^= 1; }
+            }
           }
         }
       }
@@ -141,20 +148,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
     if (lane == 0) {
       int hs = 0; uint32_t hph = 0;
       int ws = 0; uint32_t wph = 0;
-      uint32_t tph = 0;
+      uint32_t tph[2] = {0u, 0u};
       for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
         const TileInfo ti = decode_tile(P, t);
         if (ti.nstrips == 0) continue;
         const int rows = (ti.rows + 1) & ~1;
         const int nstrips = ti.nstrips;
         const uint32_t idesc = umma_idesc_f16(128, rows * kStripW);
+        const bool stag = nstrips == 2 && P.nsub >= 2;
+        uint32_t hbase = 0;
 
-        mbar_wait(tempty, tph ^ 1);   // epilogue has drained the accumulators of the previous tile
-        tc_fence_after();
-        for (int sc = 0; sc < P.nsub; ++sc) {
-          mbar_wait(&hfull[hs], hph);
-          tc_fence_after();
-          const uint32_t hbase = smem_u32(halo + hs * G::HALO_BYTES);
+        // one kernel row of weights per ring stage; strips [s0, s1) of the resident halo; `fresh`: first sub-chunk
+        auto run_rows = [&](int s0, int s1, bool fresh) {
           for (int dy = 0; dy < KS; ++dy) {
             mbar_wait(&wfull[ws], wph);
             tc_fence_after();
@@ -162,8 +167,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
 #pragma unroll
             for (int dx = 0; dx < KS; ++dx) {
               const uint64_t da = umma_smem_desc(wbase + dx * TAP_BYTES, /*LBO (K group)*/ 128 * 16, /*SBO*/ 128, 0);
-              const uint32_t acc = (sc | dy | dx) != 0;
-              for (int s = 0; s < nstrips; ++s) {
+              const uint32_t acc = (fresh && dy == 0 && dx == 0) ? 0u : 1u;
+              for (int s = s0; s < s1; ++s) {
                 const uint32_t bstart = hbase + static_cast<uint32_t>((dy * G::HWX + dx + kStripW * s) * 16);
                 const uint64_t db = umma_smem_desc(bstart, /*LBO*/ G::HWY * G::HWX * 16, /*SBO*/ G::HWX * 16, 0);
                 umma_f16(tmem_base + s * 256, da, db, idesc, acc);
@@ -172,11 +177,46 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
             umma_commit(&wempty[ws]);
             if (++ws == NUM_W) { ws = 0; wph ^= 1; }
           }
+        };
+        auto wait_halo = [&]() {
+          mbar_wait(&hfull[hs], hph);
+          tc_fence_after();
+          hbase = smem_u32(halo + hs * G::HALO_BYTES);
+        };
+        auto release_halo = [&]() {
           umma_commit(&hempty[hs]);
           if (++hs == NUM_H) { hs = 0; hph ^= 1; }
+        };
+        auto wait_acc = [&](int s) {      // epilogue has drained strip s of the previous tile
+          mbar_wait(&tempty[s], tph[s] ^ 1);
+          tc_fence_after();
+        };
+
+        if (!stag) {
+          for (int s = 0; s < nstrips; ++s) wait_acc(s);
+          for (int sc = 0; sc < P.nsub; ++sc) {
+            wait_halo();
+            run_rows(0, nstrips, sc == 0);
+            release_halo();
+          }
+          for (int s = 0; s < nstrips; ++s) { umma_commit(&tfull[s]); tph[s] ^= 1; }
+        } else {
+          wait_halo();
+          wait_acc(0); run_rows(0, 1, true);
+          wait_acc(1); run_rows(1, 2, true);
+          release_halo();
+          for (int sc = 1; sc + 1 < P.nsub; ++sc) {
+            wait_halo();
+            run_rows(0, 2, false);
+            release_halo();
+          }
+          wait_halo();
+          run_rows(0, 1, false);
+          umma_commit(&tfull[0]); tph[0] ^= 1;
+          run_rows(1, 2, false);
+          release_halo();
+          umma_commit(&tfull[1]); tph[1] ^= 1;
         }
-        umma_commit(tfull);
-        tph ^= 1;
       }
     }
   } else if (warp >= 4) {
@@ -196,7 +236,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
       const int plane = ti.plane, y0 = ti.y0, x0 = ti.x0, rows = ti.rows, nstrips = ti.nstrips;
       const int nquads = (rows + 3) >> 2;
 
-      mbar_wait(tfull, tph);
+      if (sg >= nstrips) continue;               // this strip group has no accumulator in a 1-strip tile
+      mbar_wait(&tfull[sg], tph);
       tc_fence_after();
       for (int s = sg; s < nstrips; s += 2) {
         for (int rq = 0; rq < nquads; ++rq) {
@@ -268,7 +309,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty);
+      if (lane == 0) mbar_arrive(&tempty[sg]);
       tph ^= 1;
     }
   }

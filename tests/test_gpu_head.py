@@ -130,3 +130,39 @@ def test_model_forward_api():
     N = 17 * 13
     assert loc.shape == (1, 2, 4, N) and cls.shape == (1, 2, N) and corners.shape == (1, 2, 8, N)
     assert bool(torch.isfinite(cls).all()) and float(loc.abs().max()) < 1e-4     # identity init
+
+
+def test_one_cta_correlation_variant_matches():
+    """The 1-CTA correlation main loop (OS2D_B200_CORR_1CTA=1, A/B switch of csrc/corr.cu) gives the same result as the
+    default 2-CTA (cta_group::2) variant; run in a subprocess because the switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    from _util import ROOT
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from _util import synth_inputs
+from oracle import head_oracle as ho
+from os2d_b200 import head as bh
+from os2d_b200.structures import FeatureMapSize
+tn = ho.random_transform_net(6, seed=5, spread=0.005)
+cms, fm = synth_inputs(9, 1, 21, 19, [(15, 15), (12, 18), (19, 11)])
+hc = bh.build_os2d_head_creator(False, True, True, FeatureMapSize(w=16, h=16), FeatureMapSize(w=16, h=16))
+hc.aligner.parameter_regressor.load_state_dict(dict(tn), strict=False); hc.eval()
+with torch.no_grad():
+    loc, rec, _, cor = hc.create_os2d_head([c.cuda() for c in cms])(fm.cuda())
+torch.save([loc.cpu(), rec.cpu(), cor.cpu()], sys.argv[1])
+""" % (ROOT, ROOT)
+    outs = []
+    for variant in ("2cta", "1cta"):
+        env = dict(os.environ)
+        env.pop("OS2D_B200_CORR_1CTA", None)
+        if variant == "1cta":
+            env["OS2D_B200_CORR_1CTA"] = "1"
+        path = "/tmp/os2d_b200_corr_%s.pt" % variant
+        r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append(torch.load(path))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)        # same MMA order per accumulator element => bit-identical
