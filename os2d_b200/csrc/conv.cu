@@ -15,6 +15,8 @@
 // Epilogue modes: see ConvLayerDesc in kernels.h (BN folded to fp32 alpha/beta, hi/lo weight rows combined).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -57,24 +59,8 @@ struct Params {
 
 struct TileInfo { int plane, y0, x0, rows, nstrips; };
 
-// Work list: 2-strip tiles (plane, row tile, strip pair) in order; when the last wave of the persistent grid would be
-// less than half full, its 2-strip tiles are split into 1-strip tiles so that the tail costs half a tile per CTA.
-__device__ __forceinline__ TileInfo decode_tile(const Params& P, int t) {
-  int d, s0, ns;
-  if (t < P.n_double) { d = t; s0 = 0; ns = 2; }
-  else { const int u = t - P.n_double; d = P.n_double + (u >> 1); s0 = u & 1; ns = 1; }
-  const int tiles_per_plane = P.TY * P.TXP;
-  TileInfo ti;
-  ti.plane = d / tiles_per_plane;
-  const int rem = d - ti.plane * tiles_per_plane;
-  const int ty = rem / P.TXP, txp = rem - ty * P.TXP;
-  ti.y0 = ty * P.T;
-  ti.x0 = (kStripsPerTile * txp + s0) * kStripW;
-  ti.rows = min(P.T, P.H - ti.y0);
-  const int strips_left = (P.W - ti.x0 + kStripW - 1) / kStripW;
-  ti.nstrips = max(0, min(ns, strips_left));
-  return ti;
-}
+// (Negative result, kept out of the code: staging the weight tile of a tap in TMEM with tcgen05.cp and running the MMAs in
+// TS mode is correct but slower - 1.19 vs 1.12 ms for conv1 - because the copy serialises with the MMAs in the tensor pipe.)
 
 template <int KS>
 __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant__ CUtensorMap map_in, Params P) {
@@ -145,7 +131,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) control flow converged; one elected lane issues the tcgen05 instructions.
+    // (Issuing from a divergent `lane == 0` branch makes ptxas wrap every UMMA in a uniform-register election loop.)
+    {
       int hs = 0; uint32_t hph = 0;
       int ws = 0; uint32_t wph = 0;
       uint32_t tph[2] = {0u, 0u};
@@ -156,35 +144,48 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
         const int nstrips = ti.nstrips;
         const uint32_t idesc = umma_idesc_f16(128, rows * kStripW);
         const bool stag = nstrips == 2 && P.nsub >= 2;
-        uint32_t hbase = 0;
+        uint64_t db0 = 0;
 
-        // one kernel row of weights per ring stage; strips [s0, s1) of the resident halo; `fresh`: first sub-chunk
-        auto run_rows = [&](int s0, int s1, bool fresh) {
+        // One kernel row of weights per ring stage; strips [S0, S1) (compile time) of the resident halo; `fresh`: first
+        // sub-chunk.  The issuing thread is the critical resource of this kernel (one UMMA every ~112 clocks): descriptors
+        // are formed by adding small constants to per-stage bases (the 14-bit address fields cannot carry for shared
+        // memory addresses < 256 KB), everything else is unrolled.
+        auto run_rows = [&](auto s0c, auto s1c, bool fresh) {
+          constexpr int S0 = decltype(s0c)::value, S1 = decltype(s1c)::value;
           for (int dy = 0; dy < KS; ++dy) {
             mbar_wait(&wfull[ws], wph);
             tc_fence_after();
-            const uint32_t wbase = smem_u32(wst + ws * G::WSTAGE_BYTES);
+            const uint64_t da0 = umma_smem_desc(smem_u32(wst + ws * G::WSTAGE_BYTES), /*LBO (K group)*/ 128 * 16, /*SBO*/ 128, 0);
+            const uint64_t dbr = db0 + static_cast<uint64_t>(dy * G::HWX);
+            const uint32_t acc0 = (fresh && dy == 0) ? 0u : 1u;
+            if (elect_one()) {
 #pragma unroll
             for (int dx = 0; dx < KS; ++dx) {
-              const uint64_t da = umma_smem_desc(wbase + dx * TAP_BYTES, /*LBO (K group)*/ 128 * 16, /*SBO*/ 128, 0);
-              const uint32_t acc = (fresh && dy == 0 && dx == 0) ? 0u : 1u;
-              for (int s = s0; s < s1; ++s) {
-                const uint32_t bstart = hbase + static_cast<uint32_t>((dy * G::HWX + dx + kStripW * s) * 16);
-                const uint64_t db = umma_smem_desc(bstart, /*LBO*/ G::HWY * G::HWX * 16, /*SBO*/ G::HWX * 16, 0);
+              const uint64_t da = da0 + static_cast<uint64_t>(dx * (TAP_BYTES >> 4));
+              const uint32_t acc = (dx == 0) ? acc0 : 1u;
+#pragma unroll
+              for (int s = S0; s < S1; ++s) {
+                const uint64_t db = dbr + static_cast<uint64_t>(dx + kStripW * s);
                 umma_f16(tmem_base + s * 256, da, db, idesc, acc);
               }
             }
             umma_commit(&wempty[ws]);
+            }
+            __syncwarp();
             if (++ws == NUM_W) { ws = 0; wph ^= 1; }
           }
         };
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        using I2 = std::integral_constant<int, 2>;
         auto wait_halo = [&]() {
           mbar_wait(&hfull[hs], hph);
           tc_fence_after();
-          hbase = smem_u32(halo + hs * G::HALO_BYTES);
+          db0 = umma_smem_desc(smem_u32(halo + hs * G::HALO_BYTES), /*LBO*/ G::HWY * G::HWX * 16, /*SBO*/ G::HWX * 16, 0);
         };
         auto release_halo = [&]() {
-          umma_commit(&hempty[hs]);
+          if (elect_one()) umma_commit(&hempty[hs]);
+          __syncwarp();
           if (++hs == NUM_H) { hs = 0; hph ^= 1; }
         };
         auto wait_acc = [&](int s) {      // epilogue has drained strip s of the previous tile
@@ -196,26 +197,28 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
           for (int s = 0; s < nstrips; ++s) wait_acc(s);
           for (int sc = 0; sc < P.nsub; ++sc) {
             wait_halo();
-            run_rows(0, nstrips, sc == 0);
+            if (nstrips == 2) run_rows(I0{}, I2{}, sc == 0); else run_rows(I0{}, I1{}, sc == 0);
             release_halo();
           }
-          for (int s = 0; s < nstrips; ++s) { umma_commit(&tfull[s]); tph[s] ^= 1; }
+          for (int s = 0; s < nstrips; ++s) { if (elect_one()) umma_commit(&tfull[s]); __syncwarp(); tph[s] ^= 1; }
         } else {
           wait_halo();
-          wait_acc(0); run_rows(0, 1, true);
-          wait_acc(1); run_rows(1, 2, true);
+          wait_acc(0); run_rows(I0{}, I1{}, true);
+          wait_acc(1); run_rows(I1{}, I2{}, true);
           release_halo();
           for (int sc = 1; sc + 1 < P.nsub; ++sc) {
             wait_halo();
-            run_rows(0, 2, false);
+            run_rows(I0{}, I2{}, false);
             release_halo();
           }
           wait_halo();
-          run_rows(0, 1, false);
-          umma_commit(&tfull[0]); tph[0] ^= 1;
-          run_rows(1, 2, false);
+          run_rows(I0{}, I1{}, false);
+          if (elect_one()) umma_commit(&tfull[0]);
+          __syncwarp(); tph[0] ^= 1;
+          run_rows(I1{}, I2{}, false);
           release_halo();
-          umma_commit(&tfull[1]); tph[1] ^= 1;
+          if (elect_one()) umma_commit(&tfull[1]);
+          __syncwarp(); tph[1] ^= 1;
         }
       }
     }

@@ -175,7 +175,9 @@ corr_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader CTA only in the 2-CTA variant) ------------------------------
-    if (lane == 0 && rank == 0) {
+    // The warp stays converged (warp-uniform control flow); one elected lane issues the tcgen05 instructions - issuing from
+    // a divergent `lane == 0` branch makes ptxas wrap every UMMA in a uniform-register election loop.
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(kTwoCta ? 2 * BM : BM, BN);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
@@ -186,20 +188,24 @@ corr_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * K::STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+          // 128B-swizzled K-major tiles: 8-row groups 1024 B apart, K advance = 32 B (+2 in the address field) inside the atom
+          const uint64_t da0 = umma_smem_desc(smem_u32(smem + stage * K::STAGE_BYTES), 16, 1024, 2);
+          const uint64_t db0 = umma_smem_desc(smem_u32(smem + stage * K::STAGE_BYTES) + A_BYTES, 16, 1024, 2);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // 128B-swizzled K-major tiles: 8-row groups 1024 B apart, K advance = 32 B inside the atom
-            const uint64_t da = umma_smem_desc(sa + k * 32, 16, 1024, 2);
-            const uint64_t db = umma_smem_desc(sb + k * 32, 16, 1024, 2);
-            if constexpr (kTwoCta) umma_f16_2sm(d_tmem, da, db, idesc, (kb | k) != 0);
-            else umma_f16(d_tmem, da, db, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint32_t acc = (k == 0) ? (kb != 0 ? 1u : 0u) : 1u;
+              if constexpr (kTwoCta) umma_f16_2sm(d_tmem, da0 + 2 * k, db0 + 2 * k, idesc, acc);
+              else umma_f16(d_tmem, da0 + 2 * k, db0 + 2 * k, idesc, acc);
+            }
+            if constexpr (kTwoCta) umma_commit_2sm(&empty[stage]); else umma_commit(&empty[stage]);
+            if (kb == KB - 1) {
+              if constexpr (kTwoCta) umma_commit_2sm(&tfull[as]); else umma_commit(&tfull[as]);
+            }
           }
-          if constexpr (kTwoCta) umma_commit_2sm(&empty[stage]); else umma_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if constexpr (kTwoCta) umma_commit_2sm(&tfull[as]); else umma_commit(&tfull[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
