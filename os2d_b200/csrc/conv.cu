@@ -59,6 +59,25 @@ struct Params {
 
 struct TileInfo { int plane, y0, x0, rows, nstrips; };
 
+// Work list: 2-strip tiles (plane, row tile, strip pair) in order; when the last wave of the persistent grid would be
+// less than half full, its 2-strip tiles are split into 1-strip tiles so that the tail costs half a tile per CTA.
+__device__ __forceinline__ TileInfo decode_tile(const Params& P, int t) {
+  int d, s0, ns;
+  if (t < P.n_double) { d = t; s0 = 0; ns = 2; }
+  else { const int u = t - P.n_double; d = P.n_double + (u >> 1); s0 = u & 1; ns = 1; }
+  const int tiles_per_plane = P.TY * P.TXP;
+  TileInfo ti;
+  ti.plane = d / tiles_per_plane;
+  const int rem = d - ti.plane * tiles_per_plane;
+  const int ty = rem / P.TXP, txp = rem - ty * P.TXP;
+  ti.y0 = ty * P.T;
+  ti.x0 = (kStripsPerTile * txp + s0) * kStripW;
+  ti.rows = min(P.T, P.H - ti.y0);
+  const int strips_left = (P.W - ti.x0 + kStripW - 1) / kStripW;
+  ti.nstrips = max(0, min(ns, strips_left));
+  return ti;
+}
+
 // (Negative result, kept out of the code: staging the weight tile of a tap in TMEM with tcgen05.cp and running the MMAs in
 // TS mode is correct but slower - 1.19 vs 1.12 ms for conv1 - because the copy serialises with the MMAs in the tensor pipe.)
 
