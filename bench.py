@@ -377,7 +377,7 @@ def run_ours(args):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
     except Exception:   # noqa: BLE001
         traffic = {}
-    kernel_names = {"conv1": "conv::conv_kernel<7>", "conv2": "conv::conv_kernel<5>", "corr": "corr::corr_kernel"}
+    kernel_names = {"conv1": "conv::conv_kernel<7>", "conv2": "conv::conv_kernel<5>", "corr": "corr::corr_kernel<1>"}
 
     def roof(name, flop):
         ms = stage_avg.get(name)
