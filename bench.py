@@ -12,7 +12,6 @@ input through a stride-16 C4 backbone, which is outside the path) against C quer
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The kernels are built in-tree (git-ignored): rebuild when a fresh checkout has no library yet and nvcc exists.
+    This is test infrastructure - the package itself never builds or falls back silently."""
+    lib = os.path.join(ROOT, "os2d_b200", "libos2d_b200.so")
+    if not os.path.exists(lib) and os.path.exists("/usr/local/cuda/bin/nvcc"):
+        import __graft_entry__
+        __graft_entry__.build()
+    yield
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")

@@ -1,6 +1,5 @@
 """GPU parity tests proper: the CUDA path, called through the C ABI (ctypes) via the drop-in classes, against the
 committed reference golden vectors and against the CPU oracle on seeded inputs."""
-import numpy as np
 import pytest
 import torch
 

@@ -4,10 +4,9 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-import os2d_b200
 from os2d_b200 import head as bh
 from os2d_b200.structures import FeatureMapSize, BoxList, cat_boxlist
-from os2d_b200.box_coder import BoxGridGenerator, Os2dBoxCoder
+from os2d_b200.box_coder import Os2dBoxCoder
 from oracle import head_oracle as ho
 from oracle import postproc_oracle as po
 

@@ -2,7 +2,6 @@
 (run in a subprocess: install() rebinds module globals)."""
 import subprocess
 import sys
-import os
 
 import pytest
 
