@@ -5,6 +5,7 @@ Public surface mirrors the reference modules for the hot path:
     os2d_b200.box_coder  <-> os2d/modeling/box_coder.py (inference part) + bounding_box.nms
     os2d_b200.structures <-> os2d/structures/{feature_map,bounding_box}.py
     os2d_b200.model      <-> os2d/modeling/model.py (forward / apply_class_heads)
+    os2d_b200.evaluate   <-> os2d/engine/evaluate.py make_iterator_extract_scores_from_images_batched (batched classes)
     os2d_b200.dist       class-axis sharding over GPUs + all-gather of per-class outputs
     os2d_b200.install    monkey-patch hook that routes an unmodified reference main.py through these classes
 """

@@ -311,6 +311,24 @@ class Os2dHead(nn.Module):
         # optional per-stage CUDA-event timing (bench.py): list of (stage, start_event, end_event) when not None
         self.profile_events = None
 
+    def select(self, indices):
+        """Head over a subset / reordering of this head's classes (shares the aligner; no re-packing of the operand).
+        Used by the batched evaluation iterator when only some labels are searched in an image batch."""
+        idx = torch.as_tensor(indices, dtype=torch.long, device=self.class_feature_maps.device)
+        sub = Os2dHead.__new__(Os2dHead)
+        nn.Module.__init__(sub)
+        sub.class_feature_maps = self.class_feature_maps.index_select(0, idx)
+        sub._class_packed = self._class_packed.index_select(0, idx).contiguous()
+        sub.class_batch_size = int(idx.numel())
+        sub.box_grid_generator_image_level = self.box_grid_generator_image_level
+        sub.box_grid_generator_feature_map_level = self.box_grid_generator_feature_map_level
+        sub.class_pool_mask = self.class_pool_mask.index_select(0, idx)
+        sub.aligner = self.aligner
+        sub.max_planes_per_call = self.max_planes_per_call
+        sub.supports_out_views = True
+        sub.profile_events = None
+        return sub
+
     def _timed(self, name, fn, *a):
         if self.profile_events is None:
             return fn(*a)

@@ -13,6 +13,7 @@ import importlib
 
 from . import box_coder as _bc
 from . import dist as _dist
+from . import evaluate as _evaluate
 from . import head as _head
 from . import model as _model
 from . import structures as _st
@@ -29,7 +30,7 @@ def install(reference_package="os2d"):
     ref_bb = importlib.import_module(reference_package + ".structures.bounding_box")
 
     # 1. value types: use the reference's classes inside this package
-    for mod in (_st, _bc, _head, _model, _dist):
+    for mod in (_st, _bc, _head, _model, _dist, _evaluate):
         if hasattr(mod, "FeatureMapSize"):
             setattr(mod, "FeatureMapSize", ref_fm.FeatureMapSize)
         if hasattr(mod, "BoxList"):
@@ -61,6 +62,14 @@ def install(reference_package="os2d"):
     ref_bc.Os2dBoxCoder.decode_pyramid = decode_pyramid
     ref_bb.nms = _bc.nms
     ref_bc.nms = _bc.nms
+
+    # 4. batched-class evaluation iterator (evaluate.py:177; needs matplotlib/yacs importable, so only when it imports)
+    try:
+        ref_eval = importlib.import_module(reference_package + ".engine.evaluate")
+        from . import evaluate as _ev
+        ref_eval.make_iterator_extract_scores_from_images_batched = _ev.make_iterator_extract_scores_from_images_batched
+    except Exception:   # noqa: BLE001  - the reference's eval module is not importable without matplotlib / yacs
+        pass
     _installed = True
     return True
 

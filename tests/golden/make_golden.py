@@ -137,7 +137,83 @@ def make_nms_golden():
     print("nms golden: kept", keep.numel(), "of", n)
 
 
+MODEL_SEED = 7
+
+
+class FakeLoader:
+    """The part of DataloaderOneShotDetection (os2d/data/dataloader.py:146) the evaluation iterator touches."""
+
+    def __init__(self, class_images, class_ids, pyramids, image_ids, target_sizes, ref_types=True):
+        self.class_images, self.class_ids = class_images, class_ids
+        self.pyramids, self.image_ids, self.target_sizes = pyramids, image_ids, target_sizes
+
+    def get_all_class_images(self):
+        ratios = [float(im.shape[-1]) / im.shape[-2] for im in self.class_images]
+        return self.class_images, ratios, self.class_ids
+
+    def make_iterator_for_all_images(self, batch_size, num_random_pyramid_scales=0):
+        # one batch holding every image; box transforms: one TransformList per (image, level)
+        transforms = []
+        for tgt in self.target_sizes:
+            per_level = []
+            for _ in self.pyramids:
+                t = TransformList()
+                t.append(lambda boxes, tgt=tgt: boxes.resize(tgt))
+                per_level.append(t)
+            transforms.append(per_level)
+        yield self.image_ids, self.pyramids, transforms, self.target_sizes
+
+
+def eval_iterator_inputs():
+    g = torch.Generator().manual_seed(55)
+    class_images = [torch.randn(1, 3, 64, 80, generator=g), torch.randn(1, 3, 96, 48, generator=g),
+                    torch.randn(1, 3, 72, 72, generator=g)]
+    class_ids = [4, 9, 2]
+    pyramids = [torch.randn(2, 3, 96, 128, generator=g), torch.randn(2, 3, 128, 176, generator=g)]
+    return class_images, class_ids, pyramids
+
+
+def make_eval_iterator_golden():
+    """Runs the UNMODIFIED reference iterator (class_batch_size = 1 loop, evaluate.py:177-371) on CPU with a fake
+    dataloader; the model weights are regenerated from MODEL_SEED by the test (checksum stored)."""
+    import types
+    import logging
+    sys.modules.setdefault("os2d.utils.visualization", types.ModuleType("os2d.utils.visualization"))
+    from os2d.engine.evaluate import make_iterator_extract_scores_from_images_batched as ref_iterator
+    from os2d.modeling.model import Os2dModel
+    torch.cuda.synchronize = lambda *a, **k: None          # evaluate.py:312,332 call it unguarded; CPU run here
+    torch.manual_seed(MODEL_SEED)
+    net = Os2dModel(logger=logging.getLogger("golden"), is_cuda=False, backbone_arch="resnet50",
+                    merge_branch_parameters=True, use_inverse_geom_model=True, simplify_affine=False)
+    tn = ho.random_transform_net(6, seed=TN_SEED, spread=TN_SPREAD)
+    sd = dict(tn)
+    sd["conv.1.num_batches_tracked"] = torch.tensor(0)
+    sd["conv.4.num_batches_tracked"] = torch.tensor(0)
+    net.os2d_head_creator.aligner.parameter_regressor.load_state_dict(sd)
+    net.eval()
+    backbone_checksum = float(sum(v.double().abs().sum() for k, v in net.net_feature_maps.state_dict().items()
+                                  if v.dtype.is_floating_point))
+    class_images, class_ids, pyramids = eval_iterator_inputs()
+    tgt = FeatureMapSize(w=352, h=256)
+    loader = FakeLoader(class_images, class_ids, pyramids, [10, 11], [tgt, tgt])
+    out = {"backbone_checksum": np.float64(backbone_checksum), "model_seed": np.int64(MODEL_SEED)}
+    torch.set_grad_enabled(False)       # evaluate() runs the iterator under @torch.no_grad() (evaluate.py:20)
+    for rec in ref_iterator(loader, net, logging.getLogger("golden"), image_batch_size=2, is_cuda=False,
+                            class_image_augmentation="horflip"):
+        image_id, loc_p, cls_p, pyr, q_sizes, b_class_ids, rev, fm_sizes, corners_p = rec
+        for lvl in range(len(loc_p)):
+            out["img%d_loc_%d" % (image_id, lvl)] = loc_p[lvl].numpy()
+            out["img%d_cls_%d" % (image_id, lvl)] = cls_p[lvl].numpy()
+            out["img%d_corners_%d" % (image_id, lvl)] = corners_p[lvl].numpy()
+            out["img%d_fm_%d" % (image_id, lvl)] = np.array([fm_sizes[lvl].w, fm_sizes[lvl].h])
+        out["img%d_class_ids" % image_id] = np.array(b_class_ids)
+        out["img%d_query_sizes" % image_id] = np.array([[s.w, s.h] for s in q_sizes])
+    np.savez_compressed(os.path.join(HERE, "eval_iterator.npz"), **out)
+    print("eval iterator golden:", sorted(k for k in out if k.startswith("img10"))[:4], "backbone checksum", backbone_checksum)
+
+
 if __name__ == "__main__":
     make_head_goldens()
     make_decode_golden()
     make_nms_golden()
+    make_eval_iterator_golden()
