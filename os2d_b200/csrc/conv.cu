@@ -366,6 +366,14 @@ static int launch_t(const ConvLayerDesc& L, const void* in_vol, const void* wblo
   const int nty = (H + kMaxTileRows - 1) / kMaxTileRows;
   int T = (H + nty - 1) / nty;
   T = (T + 1) & ~1;
+  // Small problems (fewer 2-strip tiles than SMs, e.g. 512 px x 4 classes = 8 tiles): fill the machine instead - every
+  // tile becomes a 1-strip tile and the tile height shrinks (not below 8 rows) until there is a tile per SM.
+  const int strips = (W + kStripW - 1) / kStripW;
+  bool all_single = false;
+  if (static_cast<long>(planes) * ((H + T - 1) / T) * P.TXP < num_sms) {
+    all_single = true;
+    while (T > 8 && static_cast<long>(planes) * ((H + T - 1) / T) * strips < num_sms) T -= 2;
+  }
   if (const char* ev = getenv("OS2D_B200_CONV_TILE_ROWS")) {   // tuning override (even, 2..32)
     const int v = atoi(ev);
     if (v >= 2 && v <= kMaxTileRows && (v & 1) == 0) T = v;
@@ -380,6 +388,7 @@ static int launch_t(const ConvLayerDesc& L, const void* in_vol, const void* wblo
     const bool split = rem > 0 && 2 * rem <= grid_sz;
     P.n_double = split ? doubles - rem : doubles;
     P.total_tiles = split ? doubles + rem : doubles;
+    if (all_single) { P.n_double = 0; P.total_tiles = 2 * doubles; }
     if (getenv("OS2D_B200_CONV_NO_TAIL_SPLIT")) { P.n_double = doubles; P.total_tiles = doubles; }
   }
   P.nsub = L.in_chunks16;
