@@ -75,6 +75,19 @@ int os2d_resample_boxes(const void* rawvol, const float* params, int planes, int
                         float* corners, long long score_plane_stride, long long loc_plane_stride,
                         long long corners_plane_stride, void* stream);
 
+/* ---- secondary entry points: the public methods of the reference classes that take / return the large tensors ----
+ * os2d_pack_corr_maps:     fp32 correlation maps [planes,225,H*W] -> zvol / rawvol (TransformationNet.forward input side,
+ *                          head.py:648-650); then os2d_transform_conv 1..3 give the parameters.
+ * os2d_affine_grids:       params [planes,P,H*W] -> grids [planes,H*W,15,15,2] fp32 in local coordinates
+ *                          (Os2dAlignment.forward, head.py:155-193).
+ * os2d_resample_with_grid: Os2dHead.resample_of_correlation_map_fast/_simple (head.py:439-594): corr fp32
+ *                          [planes,225,H*W], grids [planes,H*W,15,15,2] in [-1,1] unit coordinates of the feature map,
+ *                          mask [C,225] -> pooled [planes,H*W] (plane = image * C + class). */
+int os2d_pack_corr_maps(const float* corr, int planes, int H, int W, void* zvol, void* rawvol, void* stream);
+int os2d_affine_grids(const float* params, int planes, int P, int H, int W, int inverse, float* grids, void* stream);
+int os2d_resample_with_grid(const float* corr, const float* grids, const float* mask, int planes, int C, int H, int W,
+                            float* out, void* stream);
+
 /* ---- K4: decode + filter, all classes of one pyramid level (box_coder.py:490-520) ---------------------
  *   loc [C,4,N], score [C,N], corners [C,8,N] or NULL -> boxes [C,N,4], anchors [N,4], corners_out [C,N,8],
  *   valid [C,N] (score > thr and non-empty after clipping); boxes/anchors/corners are rescaled to the

@@ -125,6 +125,22 @@ int os2d_resample_boxes(const void* rawvol, const float* params, int planes, int
                          score_plane_stride, loc_plane_stride, corners_plane_stride, static_cast<cudaStream_t>(stream));
 }
 
+int os2d_pack_corr_maps(const float* corr, int planes, int H, int W, void* zvol, void* rawvol, void* stream) {
+  if (!corr || !zvol || !rawvol) return kErrBadArg;
+  return launch_pack_corr(corr, planes, H * W, zvol, rawvol, static_cast<cudaStream_t>(stream));
+}
+
+int os2d_affine_grids(const float* params, int planes, int P, int H, int W, int inverse, float* grids, void* stream) {
+  if (!params || !grids) return kErrBadArg;
+  return launch_affine_grids(params, planes, P, H * W, inverse, grids, static_cast<cudaStream_t>(stream));
+}
+
+int os2d_resample_with_grid(const float* corr, const float* grids, const float* mask, int planes, int C, int H, int W,
+                            float* out, void* stream) {
+  if (!corr || !grids || !mask || !out) return kErrBadArg;
+  return launch_resample_grid(corr, grids, mask, planes, C, H, W, out, static_cast<cudaStream_t>(stream));
+}
+
 int os2d_decode_boxes(int C, int N, int fm_w, float stride_w, float stride_h, float box_w, float box_h, float img_w,
                       float img_h, float score_thr, float scale_x, float scale_y, int same_scale, const float* loc,
                       const float* score, const float* corners, float* boxes, float* anchors, float* corners_out,

@@ -48,6 +48,12 @@ int launch_resample(const void* rawvol, const float* params, int planes, int P, 
                     float stride_w, float stride_h, float box_w, float box_h, float* score, float* loc,
                     float* corners, long long score_ps, long long loc_ps, long long corners_ps, cudaStream_t st);
 
+// secondary entry points (aux.cu): stand-alone TransformationNet / Os2dAlignment / resample_of_correlation_map_* methods
+int launch_pack_corr(const float* corr, int planes, int N, void* zvol, void* rawvol, cudaStream_t st);
+int launch_affine_grids(const float* params, int planes, int P, int N, int inverse, float* grid, cudaStream_t st);
+int launch_resample_grid(const float* corr, const float* grid, const float* mask, int planes, int C, int H, int W, float* out,
+                         cudaStream_t st);
+
 // post-processing
 struct DecodeArgs {
   int C, N, fm_w;                 // classes, anchors (= fm_h * fm_w), feature-map width

@@ -111,8 +111,49 @@ class TransformationNet(nn.Module):
         return self._packed
 
     def forward(self, corr_maps):
-        raise NotImplementedError("os2d_b200.TransformationNet runs fused inside Os2dHead.forward (the fp32 correlation "
-                                  "volume it would take as input is never materialised)")
+        """corr_maps [NB,225,H,W] fp32 -> transform parameters [NB,P,H,W] (head.py:648-655).  Stand-alone entry point
+        (Os2dHead.forward never builds the fp32 correlation volume): the maps are normalised / packed by
+        os2d_pack_corr_maps and run through the same three convolution kernels as the fused path."""
+        _require_inference(corr_maps, self)
+        NB, ch, H, W = corr_maps.shape
+        assert ch == CORR_CH
+        lib = _cabi.load()
+        st = _cabi.stream_ptr()
+        dev = corr_maps.device
+        N = H * W
+        corr = corr_maps.detach().to(torch.float32).contiguous()
+        zvol = torch.empty(NB, Z_CHUNKS, N, 8, dtype=torch.float16, device=dev)
+        rawvol = torch.empty(NB, CORR_CH, N, dtype=torch.float16, device=dev)
+        _cabi.check(lib.os2d_pack_corr_maps(_cabi.ptr(corr), NB, H, W, _cabi.ptr(zvol), _cabi.ptr(rawvol), st),
+                    "os2d_pack_corr_maps")
+        return run_transform_convs(self.packed_weights(), self.output_dim, zvol, NB, H, W).view(NB, self.output_dim, H, W)
+
+
+def _require_inference(t, module):
+    if torch.is_grad_enabled() and (t.requires_grad or any(p.requires_grad for p in module.parameters())):
+        raise RuntimeError("os2d_b200 implements inference only; call it under torch.no_grad() "
+                           "(training / autograd through the head is out of scope and has no fallback)")
+    if t.device.type != "cuda":
+        raise RuntimeError("os2d_b200 requires CUDA tensors (no CPU path)")
+
+
+def run_transform_convs(pw, P, zvol, planes, H, W, timed=None):
+    """z volume [planes,30,N,8] -> parameters [planes,P,N] through the three conv kernels (os2d_transform_conv 1..3)."""
+    lib = _cabi.load()
+    st = _cabi.stream_ptr()
+    dev = zvol.device
+    N = H * W
+    call = timed if timed is not None else (lambda name, fn, *a: fn(*a))
+    h1 = torch.empty(planes, 16, N, 8, dtype=torch.float16, device=dev)
+    h2 = torch.empty(planes, 16, N, 8, dtype=torch.float16, device=dev)
+    params = torch.empty(planes, P, N, dtype=torch.float32, device=dev)
+    _cabi.check(call("conv1", lib.os2d_transform_conv, 1, 128, _cabi.ptr(zvol), _cabi.ptr(pw["w1"]), _cabi.ptr(pw["alpha1"]),
+                     _cabi.ptr(pw["beta1"]), _cabi.ptr(h1), planes, H, W, st), "os2d_transform_conv(1)")
+    _cabi.check(call("conv2", lib.os2d_transform_conv, 2, 64, _cabi.ptr(h1), _cabi.ptr(pw["w2"]), _cabi.ptr(pw["alpha2"]),
+                     _cabi.ptr(pw["beta2"]), _cabi.ptr(h2), planes, H, W, st), "os2d_transform_conv(2)")
+    _cabi.check(call("conv3", lib.os2d_transform_conv, 3, P, _cabi.ptr(h2), _cabi.ptr(pw["w3"]), _cabi.ptr(pw["alpha3"]),
+                     _cabi.ptr(pw["beta3"]), _cabi.ptr(params), planes, H, W, st), "os2d_transform_conv(3)")
+    return params
 
 
 def pack_transform_net(sd, out_dim, device):
@@ -213,9 +254,34 @@ class Os2dAlignment(nn.Module):
                                                      normalization='batchnorm', kernel_sizes=[7, 5], channels=[128, 64],
                                                      input_feature_dim=self.input_feature_dim)
 
+    def prepare_transform_parameters_for_grid_sampler(self, transform_parameters):
+        """[NB,P,H,W] -> [NB*H*W, 2, 3] affine matrices, inverted when use_inverse_geom_model (head.py:81-153; closed-form
+        inverse instead of the batched LU).  Small tensor utility of the stand-alone API (elementwise torch ops); the
+        fused path forms theta in registers (csrc/resample.cu)."""
+        p = transform_parameters.permute(0, 2, 3, 1).reshape(-1, transform_parameters.size(1))
+        z = torch.zeros_like(p[:, 0])
+        if self.model_type == "affine":
+            assert p.size(1) == 6, "Affine tranformation parameter vector has to be of dimension 6"
+            a, b, tx, c, d, ty = (p[:, i] for i in range(6))
+        else:
+            assert p.size(1) == 4, "Simplified affine tranformation parameter vector has to be of dimension 4"
+            a, b, tx, c, d, ty = p[:, 0], z, p[:, 1], z, p[:, 2], p[:, 3]
+        if self.use_inverse_geom_model:
+            det = a * d - b * c
+            a, b, c, d = d / det, -b / det, -c / det, a / det
+            tx, ty = -(a * tx + b * ty), -(c * tx + d * ty)
+        return torch.stack([a, b, tx, c, d, ty], dim=1).view(-1, 2, 3)
+
     def forward(self, corr_maps):
-        raise NotImplementedError("os2d_b200.Os2dAlignment is fused into Os2dHead.forward; the "
-                                  "[N,H,W,15,15,2] grid tensor of the reference is never materialised")
+        """corr_maps [NB,225,H,W] -> grids of transformed points [NB,H,W,15,15,2] in the local coordinate system of every
+        location (head.py:155-193).  Stand-alone entry point: the fused path never materialises this tensor."""
+        params = self.parameter_regressor(corr_maps)
+        NB, P, H, W = params.shape
+        lib = _cabi.load()
+        grids = torch.empty(NB, H, W, GRID, GRID, 2, dtype=torch.float32, device=params.device)
+        _cabi.check(lib.os2d_affine_grids(_cabi.ptr(params.contiguous()), NB, P, H, W, 1 if self.use_inverse_geom_model else 0,
+                                          _cabi.ptr(grids), _cabi.stream_ptr()), "os2d_affine_grids")
+        return grids
 
 
 class Os2dHeadCreator(nn.Module):
@@ -389,21 +455,10 @@ class Os2dHead(nn.Module):
             planes = B * cc
             zvol = torch.empty(planes, Z_CHUNKS, N, 8, dtype=torch.float16, device=dev)
             rawvol = torch.empty(planes, CORR_CH, N, dtype=torch.float16, device=dev)
-            h1 = torch.empty(planes, 16, N, 8, dtype=torch.float16, device=dev)
-            h2 = torch.empty(planes, 16, N, 8, dtype=torch.float16, device=dev)
-            params = torch.empty(planes, P, N, dtype=torch.float32, device=dev)
             cls = self._class_packed[c0:c0 + cc]
             _cabi.check(self._timed("corr", lib.os2d_correlate, _cabi.ptr(img_packed), _cabi.ptr(cls), B, cc, D, H, W,
                                     _cabi.ptr(zvol), _cabi.ptr(rawvol), st), "os2d_correlate")
-            _cabi.check(self._timed("conv1", lib.os2d_transform_conv, 1, 128, _cabi.ptr(zvol), _cabi.ptr(pw["w1"]),
-                                    _cabi.ptr(pw["alpha1"]), _cabi.ptr(pw["beta1"]), _cabi.ptr(h1), planes, H, W, st),
-                        "os2d_transform_conv(1)")
-            _cabi.check(self._timed("conv2", lib.os2d_transform_conv, 2, 64, _cabi.ptr(h1), _cabi.ptr(pw["w2"]),
-                                    _cabi.ptr(pw["alpha2"]), _cabi.ptr(pw["beta2"]), _cabi.ptr(h2), planes, H, W, st),
-                        "os2d_transform_conv(2)")
-            _cabi.check(self._timed("conv3", lib.os2d_transform_conv, 3, P, _cabi.ptr(h2), _cabi.ptr(pw["w3"]),
-                                    _cabi.ptr(pw["alpha3"]), _cabi.ptr(pw["beta3"]), _cabi.ptr(params), planes, H, W, st),
-                        "os2d_transform_conv(3)")
+            params = run_transform_convs(pw, P, zvol, planes, H, W, timed=self._timed)
             # K3 writes straight into the final tensors (or into caller-provided views, e.g. this rank's slice of the
             # all-gather buffer): one launch when the planes of this chunk are contiguous in the output, else one per image
             if cc == C and out_views is None:
@@ -423,8 +478,22 @@ class Os2dHead(nn.Module):
 
     @staticmethod
     def resample_of_correlation_map_fast(corr_maps, resampling_grids_grid_coord, class_pool_mask):
-        raise NotImplementedError("fused into Os2dHead.forward (csrc/resample.cu); the explicit-grid entry point of the "
-                                  "reference (head.py:439-520) has no standalone kernel")
+        """corr_maps [B,C,225,H,W], grids [B,C,H,W,15,15,2] (unit coordinates of the feature map), mask [C,1,15,15] ->
+        pooled matches [B,C,1,H,W] (head.py:439-520; `_simple` :523-594 computes the same quantity).  Stand-alone entry
+        point with explicit tensors; Os2dHead.forward fuses grid generation and sampling instead."""
+        if corr_maps.device.type != "cuda":
+            raise RuntimeError("os2d_b200 requires CUDA tensors (no CPU path)")
+        B, C, ch, H, W = corr_maps.shape
+        assert ch == CORR_CH and tuple(resampling_grids_grid_coord.shape) == (B, C, H, W, GRID, GRID, 2), \
+            "the number of channels in the correlation map should match the size of the resampling grid"
+        lib = _cabi.load()
+        corr = corr_maps.detach().to(torch.float32).contiguous()
+        grids = resampling_grids_grid_coord.detach().to(torch.float32).contiguous()
+        mask = class_pool_mask.detach().to(torch.float32).reshape(C, CORR_CH).contiguous()
+        out = torch.empty(B, C, 1, H, W, dtype=torch.float32, device=corr.device)
+        _cabi.check(lib.os2d_resample_with_grid(_cabi.ptr(corr), _cabi.ptr(grids), _cabi.ptr(mask), B * C, C, H, W,
+                                                _cabi.ptr(out), _cabi.stream_ptr()), "os2d_resample_with_grid")
+        return out
 
     resample_of_correlation_map_simple = resample_of_correlation_map_fast
 
