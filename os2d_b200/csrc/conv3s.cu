@@ -18,12 +18,16 @@ constexpr int HX = 24, HY = 16;          // input halo box
 constexpr int OX = HX - 4, OY = HY - 4;  // output tile 20 x 12
 constexpr int HPIX = HX * HY;            // 384 = 3 * 128
 constexpr int IN_CHUNKS = 16;            // 8 hi + 8 lo chunk8 planes of h2
-constexpr uint32_t A_BYTES = IN_CHUNKS * HPIX * 16;   // 98304
+constexpr int KSTEPS = IN_CHUNKS / 2;      // 8 K steps of 16 channels per tile: 0..3 = h2 value, 4..7 = h2 residual
+constexpr int STAGES = 10;                // ring of K-step stages: the loads of tile t+1 stream in under the MMAs and the
+                                          // epilogue of tile t
+constexpr uint32_t STAGE_BYTES = 2 * HPIX * 16;       // 12288: [2 chunk8][HY][HX][8] fp16
+constexpr uint32_t A_BYTES = STAGES * STAGE_BYTES;    // 122880
 constexpr int NPAD_MAX = 160;
 constexpr uint32_t B_BYTES_MAX = 16 * NPAD_MAX * 16;  // w_hi (8 chunks) + w_lo (8 chunks)
 constexpr int RS_MAX = 31;                            // staging row stride (floats), odd => conflict free
 constexpr uint32_t S_BYTES = HPIX * RS_MAX * 4;
-constexpr uint32_t SMEM_BYTES = A_BYTES + B_BYTES_MAX + S_BYTES + 256 + 128;
+constexpr uint32_t SMEM_BYTES = A_BYTES + B_BYTES_MAX + S_BYTES + 512 + 128;
 
 struct Params {
   int planes, H, W, P;
@@ -37,13 +41,15 @@ struct Params {
 
 __global__ void __launch_bounds__(THREADS, 1) conv3s_kernel(const __grid_constant__ CUtensorMap map_in, Params P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  // aligned by offsetting the __shared__ pointer itself (integer round-trips of the pointer lose the address space and
+  // turn every staging access into a generic LD/ST)
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   uint8_t* sa = smem;
   uint8_t* sb = sa + A_BYTES;
   float* S = reinterpret_cast<float*>(sb + B_BYTES_MAX);
-  uint64_t* afull = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(S) + S_BYTES);
-  uint64_t* aempty = afull + 1;
-  uint64_t* tfull = aempty + 1;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(S) + S_BYTES);   // [STAGES]
+  uint64_t* aempty = afull + STAGES;                                                          // [STAGES]
+  uint64_t* tfull = aempty + STAGES;
   uint64_t* tempty = tfull + 1;
   uint64_t* wfull = tempty + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
@@ -51,7 +57,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3s_kernel(const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) tma_prefetch_desc(&map_in);
   if (warp == 1 && lane == 0) {
-    mbar_init(afull, 1); mbar_init(aempty, 1); mbar_init(tfull, 1); mbar_init(tempty, 12); mbar_init(wfull, 1);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(afull + i, 1); mbar_init(aempty + i, 1); }
+    mbar_init(tfull, 1); mbar_init(tempty, 12); mbar_init(wfull, 1);
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -66,44 +73,53 @@ __global__ void __launch_bounds__(THREADS, 1) conv3s_kernel(const __grid_constan
     if (lane == 0) {
       mbar_expect_tx(wfull, b_bytes);
       bulk_load_1d(sb, P.wblob, b_bytes, wfull);
-      uint32_t ph = 0;
+      uint32_t st = 0, ph = 0;
       for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
         const int plane = t / tiles_per_plane, rem = t - plane * tiles_per_plane;
         const int ty = rem / P.TX, tx = rem - ty * P.TX;
-        mbar_wait(aempty, ph ^ 1);
-        mbar_expect_tx(afull, A_BYTES);
-        tma_load_4d(sa, &map_in, afull, 8 * (tx * OX - 2), ty * OY - 2, 0, plane);
-        ph ^= 1;
+        for (int ks = 0; ks < KSTEPS; ++ks) {             // chunk pair 2 ks (chunks 0..7 value, 8..15 residual)
+          mbar_wait(aempty + st, ph ^ 1);
+          mbar_expect_tx(afull + st, STAGE_BYTES);
+          tma_load_4d(sa + st * STAGE_BYTES, &map_in, afull + st, 8 * (tx * OX - 2), ty * OY - 2, 2 * ks, plane);
+          if (++st == STAGES) { st = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(128, P.NPAD);
-      const uint32_t a0 = smem_u32(sa), b0 = smem_u32(sb);
-      const uint32_t a_lbo = HPIX * 16, b_lbo = P.NPAD * 16;
-      mbar_wait(wfull, 0);
-      uint32_t ph = 0;
-      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-        mbar_wait(tempty, ph ^ 1);
-        mbar_wait(afull, ph);
+    // whole warp stays converged, one elected lane issues (a divergent `lane == 0` issue path costs ~10 SASS instr / MMA)
+    const uint32_t idesc = umma_idesc_f16(128, P.NPAD);
+    const uint32_t a0 = smem_u32(sa), b0 = smem_u32(sb);
+    const uint32_t a_lbo = HPIX * 16, b_lbo = P.NPAD * 16;
+    mbar_wait(wfull, 0);
+    uint32_t st = 0, ph = 0, tph = 0;
+    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+      mbar_wait(tempty, tph ^ 1);
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        mbar_wait(afull + st, ph);
         tc_fence_after();
-        for (int mb = 0; mb < 3; ++mb) {
+        if (elect_one()) {
+          const uint32_t a_st = a0 + st * STAGE_BYTES;
+          const int kk = ks & 3;
+          const uint64_t db_hi = umma_smem_desc(b0 + kk * 2 * b_lbo, b_lbo, 128, 0);
+          const uint64_t db_lo = umma_smem_desc(b0 + (8 + kk * 2) * b_lbo, b_lbo, 128, 0);
 #pragma unroll
-          for (int seg = 0; seg < 3; ++seg) {           // (h2 hi, w hi), (h2 hi, w lo), (h2 lo, w hi)
-            const uint32_t a_seg = a0 + (seg == 2 ? 8u * a_lbo : 0u) + mb * 128 * 16;
-            const uint32_t b_seg = b0 + (seg == 1 ? 8u * b_lbo : 0u);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {            // 16 channels = 2 chunk8 per MMA
-              const uint64_t da = umma_smem_desc(a_seg + kk * 2 * a_lbo, a_lbo, 128, 0);
-              const uint64_t db = umma_smem_desc(b_seg + kk * 2 * b_lbo, b_lbo, 128, 0);
-              umma_f16(tmem_base + mb * NPAD_MAX, da, db, idesc, (seg | kk) != 0);
+          for (int mb = 0; mb < 3; ++mb) {
+            const uint64_t da = umma_smem_desc(a_st + mb * 128 * 16, a_lbo, 128, 0);
+            if (ks < 4) {                                  // h2 value x (w hi, w lo)
+              umma_f16(tmem_base + mb * NPAD_MAX, da, db_hi, idesc, ks != 0);
+              umma_f16(tmem_base + mb * NPAD_MAX, da, db_lo, idesc, 1u);
+            } else {                                       // h2 residual x w hi
+              umma_f16(tmem_base + mb * NPAD_MAX, da, db_hi, idesc, 1u);
             }
           }
+          umma_commit(aempty + st);
         }
-        umma_commit(aempty);
-        umma_commit(tfull);
-        ph ^= 1;
+        __syncwarp();
+        if (++st == STAGES) { st = 0; ph ^= 1; }
       }
+      if (elect_one()) umma_commit(tfull);
+      __syncwarp();
+      tph ^= 1;
     }
   } else if (warp >= 4) {
     const int we = warp - 4;
@@ -176,7 +192,7 @@ int launch_conv3s(const void* h2_vol, const void* wblob, const float* bias, cons
                         static_cast<uint64_t>(planes)};
     uint64_t strides[3] = {static_cast<uint64_t>(16) * W, static_cast<uint64_t>(16) * W * H,
                            static_cast<uint64_t>(16) * W * H * IN_CHUNKS};
-    uint32_t box[4] = {8 * HX, HY, IN_CHUNKS, 1};
+    uint32_t box[4] = {8 * HX, HY, 2, 1};
     int rc = encode_tensor_map(&map_in, h2_vol, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc != kOk) return rc;
