@@ -45,6 +45,11 @@ int os2d_b200_num_sms(void);
  *   normalize = 0 returns the resized maps without the L2 normalisation (head.py:241-259 alone). */
 int os2d_pack_class_features(const float* maps, int C, int D, int h, int w, int normalize, float* cf32, void* packed,
                              void* stream);
+/* Same for a set of differently sized class maps in ONE launch (the class branch of the
+ * backbone runs once per image size, model.py:80-88; nothing is concatenated): map_ptrs = device array of C pointers to
+ * [D, h_c, w_c] fp32 maps, hw = device array [C][2] of (h_c, w_c).  Bit-identical to the uniform entry point. */
+int os2d_pack_class_features_ragged(const float* const* map_ptrs, const int* hw, int C, int D, int normalize, float* cf32,
+                                    void* packed, void* stream);
 /* Image side (head.py:339): fm [B, D, N] fp32 -> packed [B, N, D] fp16 (values * 32 / (norm + 1e-5)).
  * inv_ws: workspace of B*N floats. */
 int os2d_pack_image_features(const float* fm, int B, int D, int N, float* inv_ws, void* packed, void* stream);

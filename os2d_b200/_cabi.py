@@ -21,6 +21,8 @@ SIGNATURES = {
     "os2d_b200_num_sms": (_c_int, []),
     "os2d_pack_class_features": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
                                           _c_void_p]),
+    "os2d_pack_class_features_ragged": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
+                                                 _c_void_p]),
     "os2d_pack_image_features": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "os2d_correlate": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
                                 _c_void_p]),

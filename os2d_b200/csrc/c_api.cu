@@ -83,6 +83,12 @@ int os2d_pack_class_features(const float* maps, int C, int D, int h, int w, int 
   return launch_pack_class(maps, C, D, h, w, normalize, cf32, packed, static_cast<cudaStream_t>(stream));
 }
 
+int os2d_pack_class_features_ragged(const float* const* map_ptrs, const int* hw, int C, int D, int normalize, float* cf32,
+                                    void* packed, void* stream) {
+  if (!map_ptrs || !hw || !cf32 || !packed) return kErrBadArg;
+  return launch_pack_class_ragged(map_ptrs, hw, C, D, normalize, cf32, packed, static_cast<cudaStream_t>(stream));
+}
+
 int os2d_pack_image_features(const float* fm, int B, int D, int N, float* inv_ws, void* packed, void* stream) {
   if (!fm || !inv_ws || !packed) return kErrBadArg;
   return launch_pack_image(fm, B, D, N, inv_ws, packed, static_cast<cudaStream_t>(stream));

@@ -25,6 +25,8 @@ constexpr int kMinTileRows = 20;          // N >= 160 keeps the per-MMA shared-m
 
 int launch_pack_class(const float* maps, int C, int D, int h, int w, int normalize, float* cf32, void* packed,
                       cudaStream_t st);
+int launch_pack_class_ragged(const float* const* map_ptrs, const int* hw, int C, int D, int normalize, float* cf32,
+                             void* packed, cudaStream_t st);
 int launch_pack_image(const float* fm, int B, int D, int N, float* inv_ws, void* packed, cudaStream_t st);
 
 // correlation GEMM + ReLU/L2norm/centering epilogue

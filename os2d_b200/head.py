@@ -319,8 +319,8 @@ class Os2dHeadCreator(nn.Module):
 
 
 def _prepare_class_operands(feature_maps, normalized=True):
-    """list of [1,D,h,w] CUDA fp32 maps -> (cf32 [C,D,15,15], packed fp16 [C,240,D]) via os2d_pack_class_features.
-    Classes are grouped by (h, w) so that each group is one kernel launch."""
+    """list of [1,D,h,w] CUDA fp32 maps -> (cf32 [C,D,15,15], packed fp16 [C,240,D]): ONE kernel launch for the whole
+    (possibly ragged) set, os2d_pack_class_features_ragged; os2d_pack_class_features when the list is a sliced batch."""
     lib = _cabi.load()
     assert len(feature_maps) > 0
     dev = feature_maps[0].device
@@ -330,21 +330,35 @@ def _prepare_class_operands(feature_maps, normalized=True):
     C = len(feature_maps)
     cf32 = torch.empty(C, D, GRID, GRID, dtype=torch.float32, device=dev)
     packed = torch.empty(C, CORR_PAD, D, dtype=torch.float16, device=dev)
-    groups = {}
-    for i, fm in enumerate(feature_maps):
+    sizes = set()
+    maps = []
+    for fm in feature_maps:
         assert fm.size(0) == 1, "Can process only batches of size 1, but have {0}".format(fm.size(0))
         assert fm.size(1) == D
-        groups.setdefault((fm.size(2), fm.size(3)), []).append(i)
-    for (h, w), idx in groups.items():
-        maps = torch.cat([feature_maps[i] for i in idx], dim=0).to(dtype=torch.float32).contiguous()
-        g_cf = torch.empty(len(idx), D, GRID, GRID, dtype=torch.float32, device=dev)
-        g_pk = torch.empty(len(idx), CORR_PAD, D, dtype=torch.float16, device=dev)
-        rc = lib.os2d_pack_class_features(_cabi.ptr(maps), len(idx), D, h, w, 1 if normalized else 0, _cabi.ptr(g_cf),
-                                          _cabi.ptr(g_pk), _cabi.stream_ptr())
+        if fm.device != dev:
+            raise RuntimeError("all class feature maps must live on the same CUDA device")
+        m = fm.detach()
+        if m.dtype != torch.float32 or not m.is_contiguous():
+            m = m.to(dtype=torch.float32).contiguous()
+        maps.append(m)
+        sizes.add((m.size(2), m.size(3)))
+    norm = 1 if normalized else 0
+    if len(sizes) == 1 and all(maps[i].data_ptr() + maps[i].numel() * 4 == maps[i + 1].data_ptr() for i in range(C - 1)):
+        # slices of one contiguous [C,D,h,w] batch: uniform entry point, no descriptor upload
+        (h, w), = sizes
+        rc = lib.os2d_pack_class_features(ctypes.c_void_p(maps[0].data_ptr()), C, D, h, w, norm, _cabi.ptr(cf32),
+                                          _cabi.ptr(packed), _cabi.stream_ptr())
         _cabi.check(rc, "os2d_pack_class_features")
-        ii = torch.tensor(idx, device=dev)
-        cf32.index_copy_(0, ii, g_cf)
-        packed.index_copy_(0, ii, g_pk)
+    else:
+        # one launch over per-class pointers and sizes (the maps stay where the backbone wrote them)
+        ptrs = torch.tensor([m.data_ptr() for m in maps], dtype=torch.int64).to(dev)
+        hw = torch.tensor([[m.size(2), m.size(3)] for m in maps], dtype=torch.int32).to(dev)
+        rc = lib.os2d_pack_class_features_ragged(_cabi.ptr(ptrs), _cabi.ptr(hw), C, D, norm, _cabi.ptr(cf32),
+                                                 _cabi.ptr(packed), _cabi.stream_ptr())
+        _cabi.check(rc, "os2d_pack_class_features_ragged")
+        # the kernel reads the maps asynchronously: keep them alive until it has run on this stream
+        for m in maps:
+            m.record_stream(torch.cuda.current_stream())
     return cf32, packed
 
 

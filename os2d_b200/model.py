@@ -45,7 +45,19 @@ class LabelFeatureExtractor(nn.Module):
         self.net_class_features = feature_extractor
 
     def forward(self, class_image_list):
-        return [self.net_class_features(img.unsqueeze(0)) for img in class_image_list]
+        """list of [3,h_i,w_i] images -> list of [1,D,h_i/16,w_i/16] feature maps, in order.  The reference pushes the
+        images through the backbone one by one (model.py:80-88); here images of equal size form one batch (eval-mode
+        BatchNorm: every sample is independent), and the per-class maps are views of the batch outputs that the ragged
+        pack kernel reads in place."""
+        groups = {}
+        for i, img in enumerate(class_image_list):
+            groups.setdefault((img.size(-2), img.size(-1)), []).append(i)
+        out = [None] * len(class_image_list)
+        for idx in groups.values():
+            feats = self.net_class_features(torch.stack([class_image_list[i] for i in idx], dim=0))
+            for j, i in enumerate(idx):
+                out[i] = feats[j:j + 1]
+        return out
 
 
 class Os2dModel(nn.Module):
