@@ -124,10 +124,20 @@ def transform_net(corr, tn, emulate=False):
     return p, zq
 
 
+INVERSE_CHUNK = 256 * 256 - 1      # head.py:141 (batched_inverse splits the matrices in chunks of 65535)
+INVERSE_REG = 1e-5                  # head.py:129 (added to the diagonal of every matrix of a chunk whose inversion raised)
+
+
 def theta_from_params(p, simple_affine, inverse):
     """[NB,P,H,W] regressed parameters -> six affine coefficients (a,b,tx,c,d,ty) each [NB,H,W].
     head.py:81-153: P=6 -> [[p0,p1,p2],[p3,p4,p5]], P=4 -> [[p0,0,p1],[0,p2,p3]];
-    optional inverse of the 3x3 homogeneous matrix (closed form here, LU in the reference)."""
+    optional inverse of the 3x3 homogeneous matrix [[a,b,tx],[c,d,ty],[0,0,1]] (closed form here, LU in the reference).
+    Failure handling of the reference (head.py:123-146, `robust_inverse` inside `batched_inverse`): the matrices, in
+    (n, y, x) order, are inverted in chunks of 65535 (one chunk when there are fewer); when torch.inverse raises for a chunk
+    (some matrix has an exactly zero LU pivot = is exactly singular), 1e-5 is added to the diagonal of EVERY matrix of
+    that chunk, the homogeneous 1 included, before inverting again.  Restated with "exactly singular" = fp32 a*d - b*c == 0:
+      inverse of [[a+e,b,tx],[c,d+e,ty],[0,0,1+e]] = [[A_e^-1, -A_e^-1 t / (1+e)]], evaluated in fp64 for those chunks
+    (pinned by tests/golden/theta_singular.npz, generated by the reference on CPU)."""
     if simple_affine:
         assert p.shape[1] == 4
         z = torch.zeros_like(p[:, 0])
@@ -140,6 +150,30 @@ def theta_from_params(p, simple_affine, inverse):
         ia, ib, ic, id_ = d / det, -b / det, -c / det, a / det
         itx = -(ia * tx + ib * ty)
         ity = -(ic * tx + id_ * ty)
+        singular = (det == 0).reshape(-1)
+        if bool(singular.any()):
+            n = singular.numel()
+            flagged = torch.zeros(n, dtype=torch.bool)
+            if n >= INVERSE_CHUNK:
+                for s0 in range(0, n, INVERSE_CHUNK):
+                    if bool(singular[s0:s0 + INVERSE_CHUNK].any()):
+                        flagged[s0:s0 + INVERSE_CHUNK] = True
+            else:
+                flagged[:] = True
+            flagged = flagged.view(det.shape)
+            e = INVERSE_REG
+            ar, dr = a.double() + e, d.double() + e
+            br, cr, txr, tyr = b.double(), c.double(), tx.double(), ty.double()
+            detr = ar * dr - br * cr
+            ra, rb, rc, rd = dr / detr, -br / detr, -cr / detr, ar / detr
+            rtx = -(ra * txr + rb * tyr) / (1.0 + e)
+            rty = -(rc * txr + rd * tyr) / (1.0 + e)
+            ia = torch.where(flagged, ra.float(), ia)
+            ib = torch.where(flagged, rb.float(), ib)
+            ic = torch.where(flagged, rc.float(), ic)
+            id_ = torch.where(flagged, rd.float(), id_)
+            itx = torch.where(flagged, rtx.float(), itx)
+            ity = torch.where(flagged, rty.float(), ity)
         a, b, tx, c, d, ty = ia, ib, itx, ic, id_, ity
     return a, b, tx, c, d, ty
 

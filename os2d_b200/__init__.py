@@ -13,7 +13,8 @@ from .structures import FeatureMapSize, BoxList, cat_boxlist  # noqa: F401
 from .box_coder import BoxGridGenerator, Os2dBoxCoder, nms, make_resize_transform  # noqa: F401
 from .head import (build_os2d_head_creator, Os2dAlignment, Os2dHeadCreator, Os2dHead, TransformationNet,  # noqa: F401
                    normalize_feature_map_L2)
+from .graphed import GraphedHead  # noqa: F401
 
 __all__ = ["FeatureMapSize", "BoxList", "cat_boxlist", "BoxGridGenerator", "Os2dBoxCoder", "nms",
            "make_resize_transform", "build_os2d_head_creator", "Os2dAlignment", "Os2dHeadCreator", "Os2dHead",
-           "TransformationNet", "normalize_feature_map_L2"]
+           "TransformationNet", "normalize_feature_map_L2", "GraphedHead"]

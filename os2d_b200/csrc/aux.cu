@@ -65,12 +65,7 @@ __global__ void __launch_bounds__(128) affine_grid_kernel(const float* __restric
   float a, b, tx, c, d, ty;
   if (P == 6) { a = pp[0]; b = pp[N]; tx = pp[2 * static_cast<size_t>(N)]; c = pp[3 * static_cast<size_t>(N)]; d = pp[4 * static_cast<size_t>(N)]; ty = pp[5 * static_cast<size_t>(N)]; }
   else { a = pp[0]; b = 0.f; tx = pp[N]; c = 0.f; d = pp[2 * static_cast<size_t>(N)]; ty = pp[3 * static_cast<size_t>(N)]; }
-  if (inverse) {
-    const float det = a * d - b * c;
-    const float ia = d / det, ib = -b / det, ic = -c / det, id = a / det;
-    const float itx = -(ia * tx + ib * ty), ity = -(ic * tx + id * ty);
-    a = ia; b = ib; c = ic; d = id; tx = itx; ty = ity;
-  }
+  if (inverse) invert_affine(a, b, tx, c, d, ty);
   float2* g = reinterpret_cast<float2*>(grid) + (static_cast<size_t>(plane) * N + pix) * kCorrCh;
   for (int i = 0; i < kGrid; ++i) {
     const float yi = aux_lin15(i);

@@ -160,6 +160,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- inverse of the affine model (head.py:100-153) ---------------------------------------------------------------------
+// [[a,b,tx],[c,d,ty],[0,0,1]] -> its inverse, closed form.  Exactly singular matrices (fp32 a*d - b*c == 0, evaluated
+// without FMA contraction like the elementwise torch expression of the oracle) get the reference's failure handling
+// (robust_inverse, head.py:123-134): 1e-5 is added to the diagonal of the 3x3, homogeneous 1 included, and the inverse is
+// taken of that matrix - here in fp64 (rare branch).  The reference regularises the whole chunk of 65535 matrices that
+// contains a singular one; the other matrices of such a chunk move by ~1e-5 relative, which this code does not reproduce.
+__device__ __forceinline__ void invert_affine(float& a, float& b, float& tx, float& c, float& d, float& ty) {
+  const float det = __fsub_rn(__fmul_rn(a, d), __fmul_rn(b, c));
+  if (det != 0.f) {
+    const float ia = d / det, ib = -b / det, ic = -c / det, id = a / det;
+    const float itx = -(ia * tx + ib * ty), ity = -(ic * tx + id * ty);
+    a = ia; b = ib; c = ic; d = id; tx = itx; ty = ity;
+  } else {
+    const double e = 1e-5;
+    const double ar = static_cast<double>(a) + e, dr = static_cast<double>(d) + e, br = b, cr = c;
+    const double detr = ar * dr - br * cr;
+    const double ia = dr / detr, ib = -br / detr, ic = -cr / detr, id = ar / detr;
+    const double itx = -(ia * tx + ib * ty) / (1.0 + e), ity = -(ic * tx + id * ty) / (1.0 + e);
+    a = static_cast<float>(ia); b = static_cast<float>(ib); c = static_cast<float>(ic); d = static_cast<float>(id);
+    tx = static_cast<float>(itx); ty = static_cast<float>(ity);
+  }
+}
+
 // ---- UMMA descriptors ------------------------------------------------------------------------
 // Shared-memory matrix descriptor (sm_100 layout): start[0,14) LBO[16,30) SBO[32,46) version[46,48)=1
 // base_offset[49,52) layout[61,64) (0 none, 2 = 128B swizzle).  All byte quantities >> 4.

@@ -16,7 +16,7 @@ __device__ __forceinline__ float lin15(int i) {
   return (i < 7) ? (-1.0f + step * i) : (1.0f - step * (14 - i));
 }
 
-__global__ void __launch_bounds__(128) resample_kernel(const __half* __restrict__ raw, const float* __restrict__ params,
+__global__ void __launch_bounds__(128, 12) resample_kernel(const __half* __restrict__ raw, const float* __restrict__ params,
                                                         int P, int H, int W, int inverse, float stride_w,
                                                         float stride_h, float box_w, float box_h,
                                                         float* __restrict__ score, float* __restrict__ loc,
@@ -35,12 +35,7 @@ __global__ void __launch_bounds__(128) resample_kernel(const __half* __restrict_
   } else {
     a = pp[0]; b = 0.f; tx = pp[N]; c = 0.f; d = pp[2 * N]; ty = pp[3 * static_cast<size_t>(N)];
   }
-  if (inverse) {
-    const float det = a * d - b * c;
-    const float ia = d / det, ib = -b / det, ic = -c / det, id = a / det;
-    const float itx = -(ia * tx + ib * ty), ity = -(ic * tx + id * ty);
-    a = ia; b = ib; c = ic; d = id; tx = itx; ty = ity;
-  }
+  if (inverse) invert_affine(a, b, tx, c, d, ty);
 
   // ---- score: mean of bilinear samples at the inner 11 x 11 grid points ----
   const __half* rplane = raw + static_cast<size_t>(plane) * kCorrCh * N;

@@ -268,8 +268,21 @@ class Os2dAlignment(nn.Module):
             a, b, tx, c, d, ty = p[:, 0], z, p[:, 1], z, p[:, 2], p[:, 3]
         if self.use_inverse_geom_model:
             det = a * d - b * c
-            a, b, c, d = d / det, -b / det, -c / det, a / det
-            tx, ty = -(a * tx + b * ty), -(c * tx + d * ty)
+            ia, ib, ic, id_ = d / det, -b / det, -c / det, a / det
+            itx, ity = -(ia * tx + ib * ty), -(ic * tx + id_ * ty)
+            singular = det == 0
+            if bool(singular.any()):
+                # failure handling of the reference (robust_inverse, head.py:123-134), per matrix like csrc/common.cuh
+                e = 1e-5
+                ar, dr, br, cr = a.double() + e, d.double() + e, b.double(), c.double()
+                detr = ar * dr - br * cr
+                ra, rb, rc, rd = dr / detr, -br / detr, -cr / detr, ar / detr
+                rtx = -(ra * tx.double() + rb * ty.double()) / (1.0 + e)
+                rty = -(rc * tx.double() + rd * ty.double()) / (1.0 + e)
+                ia, ib = torch.where(singular, ra.float(), ia), torch.where(singular, rb.float(), ib)
+                ic, id_ = torch.where(singular, rc.float(), ic), torch.where(singular, rd.float(), id_)
+                itx, ity = torch.where(singular, rtx.float(), itx), torch.where(singular, rty.float(), ity)
+            a, b, c, d, tx, ty = ia, ib, ic, id_, itx, ity
         return torch.stack([a, b, tx, c, d, ty], dim=1).view(-1, 2, 3)
 
     def forward(self, corr_maps):

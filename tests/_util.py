@@ -48,3 +48,15 @@ def synth_inputs(seed, B, H, W, sizes, D=1024):
 
 def have_reference():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "os2d"))
+
+
+def singular_params(seed, NB, P, H, W, singular_at):
+    """Same seeded parameters as tests/golden/make_golden.py::singular_params (exactly singular matrices planted)."""
+    g = torch.Generator().manual_seed(seed)
+    ident = torch.tensor([1., 0, 0, 0, 1, 0] if P == 6 else [1., 0, 1, 0]).view(1, P, 1, 1)
+    p = ident + 0.2 * torch.randn(NB, P, H, W, generator=g)
+    kinds6 = [[0., 0, 0.3, 0, 0, -0.2], [1., 2, 0.1, 1, 2, 0.5], [0.5, 0.25, 0.1, 2, 1, 0.5]]
+    kinds4 = [[0., 0.3, 1.1, -0.2], [0.9, 0.1, 0., 0.5], [0., 0., 0., 0.]]
+    for i, (n, y, x) in enumerate(singular_at):
+        p[n, :, y, x] = torch.tensor((kinds6 if P == 6 else kinds4)[i % 3])
+    return p

@@ -212,8 +212,52 @@ def make_eval_iterator_golden():
     print("eval iterator golden:", sorted(k for k in out if k.startswith("img10"))[:4], "backbone checksum", backbone_checksum)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+def singular_params(seed, NB, P, H, W, singular_at):
+    """Seeded regressed parameters around identity with exactly singular matrices planted at the given (n, y, x)."""
+    g = torch.Generator().manual_seed(seed)
+    ident = torch.tensor([1., 0, 0, 0, 1, 0] if P == 6 else [1., 0, 1, 0]).view(1, P, 1, 1)
+    p = ident + 0.2 * torch.randn(NB, P, H, W, generator=g)
+    kinds6 = [[0., 0, 0.3, 0, 0, -0.2], [1., 2, 0.1, 1, 2, 0.5], [0.5, 0.25, 0.1, 2, 1, 0.5]]
+    kinds4 = [[0., 0.3, 1.1, -0.2], [0.9, 0.1, 0., 0.5], [0., 0., 0., 0.]]
+    for i, (n, y, x) in enumerate(singular_at):
+        p[n, :, y, x] = torch.tensor((kinds6 if P == 6 else kinds4)[i % 3])
+    return p
+
+
+def make_singular_theta_golden():
+    """Failure handling of the inverse geometric model (head.py:123-146): the reference's own
+    prepare_transform_parameters_for_grid_sampler on parameters with exactly singular matrices.  Case `small`: one chunk
+    (< 65535 matrices), everything regularised.  Case `chunks`: 65884 matrices = chunks of 65535 + 349 with singular
+    matrices only in the second one; only a window of rows and per-chunk checksums are stored."""
+    out = {}
+    for name, simple in (("affine", False), ("simple", True)):
+        P = 4 if simple else 6
+        hc = build_os2d_head_creator(simple, False, True, FeatureMapSize(w=16, h=16), FeatureMapSize(w=16, h=16))
+        # small
+        sing = [(0, 1, 2), (1, 3, 4), (1, 0, 0)]
+        p = singular_params(21, 2, P, 5, 7, sing)
+        with torch.no_grad():
+            th = hc.aligner.prepare_transform_parameters_for_grid_sampler(p)
+        out["small_{}_theta".format(name)] = th.numpy()
+        out["small_{}_singular".format(name)] = np.array(sing, dtype=np.int64)
+        # two chunks
+        NB, H, W = 2, 182, 181
+        sing2 = [(1, 181, 100), (1, 181, 180)]          # flat indices 65803 and 65883: second chunk only
+        p2 = singular_params(22, NB, P, H, W, sing2)
+        with torch.no_grad():
+            th2 = hc.aligner.prepare_transform_parameters_for_grid_sampler(p2).reshape(-1, 6)
+        out["chunks_{}_singular".format(name)] = np.array(sing2, dtype=np.int64)
+        out["chunks_{}_head".format(name)] = th2[:256].numpy()
+        out["chunks_{}_tail".format(name)] = th2[65535 - 128:].numpy()
+        out["chunks_{}_sum0".format(name)] = np.float64(th2[:65535].double().sum())
+    np.savez_compressed(os.path.join(HERE, "theta_singular.npz"), **out)
+    print("singular theta golden:", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
+
+
 if __name__ == "__main__":
     make_head_goldens()
     make_decode_golden()
     make_nms_golden()
     make_eval_iterator_golden()
+    make_singular_theta_golden()

@@ -1,5 +1,7 @@
 """CPU: the oracle restatement against the committed golden vectors produced by the unmodified reference
 (tests/golden/make_golden.py)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -65,3 +67,58 @@ def test_greedy_nms_edge_cases():
     s = np.array([0.5, 0.5, 0.1, 0.9], np.float32)
     # identical boxes with tied scores: the lower index wins; the degenerate box (area 0) never suppresses
     np.testing.assert_array_equal(po.greedy_nms(b, s, 0.3), [3, 0, 2])
+
+
+@pytest.mark.parametrize("name,simple", [("affine", False), ("simple", True)])
+def test_singular_transforms_follow_reference_failure_handling(name, simple):
+    """head.py:123-146: a chunk of <= 65535 matrices containing an exactly singular one is regularised as a whole
+    (+1e-5 on the diagonal of the 3x3) - against outputs of the reference's own aligner on CPU."""
+    from _util import singular_params
+    gold = np.load(os.path.join(GOLDEN, "theta_singular.npz"))
+    P = 4 if simple else 6
+
+    def theta_rows(p):
+        return torch.stack(ho.theta_from_params(p, simple, True), dim=-1).reshape(-1, 6)
+
+    # one chunk: every matrix regularised; the singular ones come out ~1e5 large (fp32 LU vs fp64 closed form: 1e-2)
+    sing = [tuple(r) for r in gold["small_{}_singular".format(name)].tolist()]
+    p = singular_params(21, 2, P, 5, 7, sing)
+    th = theta_rows(p)
+    ref = torch.from_numpy(gold["small_{}_theta".format(name)]).reshape(-1, 6)
+    assert bool(torch.isfinite(th).all())
+    srows = [(n * 5 + y) * 7 + x for (n, y, x) in sing]
+    mask = torch.ones(th.shape[0], dtype=torch.bool)
+    mask[srows] = False
+    assert ((th[mask] - ref[mask]).abs() <= 2e-5 * ref[mask].abs().clamp_min(1.0)).all()
+    assert ((th[~mask] - ref[~mask]).abs() <= 1e-2 * ref[~mask].abs().max(dim=1, keepdim=True).values).all()
+    # the regularisation is visible on the regular matrices: without it the difference is ~1e-5, well above 2e-6
+    plain = torch.stack([x.reshape(-1) for x in _plain_inverse(p, simple)], dim=1)
+    assert ((plain[mask] - ref[mask]).abs().max() > 5e-6)
+
+    # two chunks (65535 + 349), singular matrices only in the second: the first chunk is NOT regularised
+    NB, H, W = 2, 182, 181
+    sing2 = [tuple(r) for r in gold["chunks_{}_singular".format(name)].tolist()]
+    p2 = singular_params(22, NB, P, H, W, sing2)
+    th2 = theta_rows(p2)
+    head, tail = torch.from_numpy(gold["chunks_{}_head".format(name)]), torch.from_numpy(gold["chunks_{}_tail".format(name)])
+    plain2 = torch.stack([x.reshape(-1) for x in _plain_inverse(p2, simple)], dim=1)
+    assert torch.equal(th2[:65535], plain2[:65535])                       # untouched chunk = plain closed form
+    assert ((th2[:256] - head).abs() <= 3e-6 * head.abs().clamp_min(1.0)).all()
+    t_or = th2[65535 - 128:]
+    srows2 = [(n * H + y) * W + x - (65535 - 128) for (n, y, x) in sing2]
+    m2 = torch.ones(t_or.shape[0], dtype=torch.bool)
+    m2[srows2] = False
+    assert ((t_or[m2] - tail[m2]).abs() <= 2e-5 * tail[m2].abs().clamp_min(1.0)).all()
+    assert bool(torch.isfinite(t_or).all())
+    assert abs(float(th2[:65535].double().sum()) - float(gold["chunks_{}_sum0".format(name)])) < 1e-3 * 65535 * 1e-3
+
+
+def _plain_inverse(p, simple):
+    if simple:
+        z = torch.zeros_like(p[:, 0])
+        a, b, tx, c, d, ty = p[:, 0], z, p[:, 1], z, p[:, 2], p[:, 3]
+    else:
+        a, b, tx, c, d, ty = (p[:, i] for i in range(6))
+    det = a * d - b * c
+    ia, ib, ic, id_ = d / det, -b / det, -c / det, a / det
+    return ia, ib, -(ia * tx + ib * ty), ic, id_, -(ic * tx + id_ * ty)
