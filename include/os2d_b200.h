@@ -108,6 +108,14 @@ int os2d_decode_boxes(int C, int N, int fm_w, float stride_w, float stride_h, fl
 int os2d_nms_segments(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int num_segs,
                       double iou_threshold, uint8_t* keep, void* stream);
 
+/* ---- detection evaluation: matching step of calc_detection_voc_prec_rec (os2d/data/voc_eval.py:109-126) ----
+ *   det_boxes [n_det,4] xyxy fp32 (already resized to the ground-truth image size), det_img / det_label [n_det] int32;
+ *   ground truth concatenated image by image: gt_boxes [n_gt,4], gt_label [n_gt], gt_offsets [n_images+1];
+ *   gt_index [n_det]: index of the ground-truth box of the same image and label with the largest IoU (+1 on x2,y2, fp32,
+ *   first among equals), -1 when there is none or that IoU < iou_thr. */
+int os2d_voc_match(const float* det_boxes, const int* det_img, const int* det_label, const float* gt_boxes,
+                   const int* gt_label, const int* gt_offsets, int n_det, float iou_thr, int* gt_index, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

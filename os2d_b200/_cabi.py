@@ -40,6 +40,8 @@ SIGNATURES = {
     "os2d_decode_boxes": (_c_int, [_c_int, _c_int, _c_int, _c_float, _c_float, _c_float, _c_float, _c_float, _c_float,
                                    _c_float, _c_float, _c_float, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                    _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "os2d_voc_match": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_float,
+                                _c_void_p, _c_void_p]),
     "os2d_nms_segments": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, ctypes.c_double, _c_void_p, _c_void_p]),
 }
 
@@ -81,7 +83,8 @@ def check(rc, what):
 
 
 def ptr(t):
-    """Device pointer of a (contiguous) torch tensor, or None."""
+    """Device pointer of a (contiguous) torch tensor, or None.  Pass NAMED tensors: a temporary created inside the call
+    expression is returned to the caching allocator before the launch and may be handed out to the next temporary."""
     if t is None:
         return None
     assert t.is_contiguous(), "os2d_b200 kernels take contiguous tensors"

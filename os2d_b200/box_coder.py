@@ -94,7 +94,8 @@ def _segmented_chunked_nms(xyxy, scores, cand, counts, iou_thr):
         perm = torch.sort(key, stable=True)[1]
         order = cand[perm].to(torch.int32).contiguous()
         keep = torch.empty(total, dtype=torch.uint8, device=dev)
-        rc = lib.os2d_nms_segments(_cabi.ptr(xyxy), _cabi.ptr(order), _cabi.ptr(seg_off.to(dev)), n_labels,
+        seg_off_dev = seg_off.to(dev)        # named: device temporaries must outlive the asynchronous launch
+        rc = lib.os2d_nms_segments(_cabi.ptr(xyxy), _cabi.ptr(order), _cabi.ptr(seg_off_dev), n_labels,
                                    float(iou_thr), _cabi.ptr(keep), _cabi.stream_ptr())
         _cabi.check(rc, "os2d_nms_segments")
         return cand[perm][keep.bool()]

@@ -169,4 +169,11 @@ int os2d_nms_segments(const float* boxes, const int32_t* order, const int32_t* s
   return launch_nms(boxes, order, seg_offsets, num_segs, iou_threshold, keep, static_cast<cudaStream_t>(stream));
 }
 
+int os2d_voc_match(const float* det_boxes, const int* det_img, const int* det_label, const float* gt_boxes,
+                   const int* gt_label, const int* gt_offsets, int n_det, float iou_thr, int* gt_index, void* stream) {
+  if (n_det > 0 && (!det_boxes || !det_img || !det_label || !gt_offsets || !gt_index)) return kErrBadArg;
+  return launch_voc_match(det_boxes, det_img, det_label, gt_boxes, gt_label, gt_offsets, n_det, iou_thr, gt_index,
+                          static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

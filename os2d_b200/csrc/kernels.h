@@ -70,6 +70,10 @@ int launch_decode(const DecodeArgs& A, const float* loc, const float* score, con
 int launch_nms(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int num_segs, double iou_thr,
                uint8_t* keep, cudaStream_t st);
 
+// detection evaluation (voc.cu)
+int launch_voc_match(const float* det_boxes, const int* det_img, const int* det_label, const float* gt_boxes,
+                     const int* gt_label, const int* gt_offsets, int n_det, float iou_thr, int* gt_index, cudaStream_t st);
+
 size_t conv_weight_blob_bytes(int ksize, int in_chunks16);
 
 // scatter-form last layer (conv3s.cu): h2 volume [planes][16 chunk8][H*W][8] -> params fp32 [planes][P][H*W]

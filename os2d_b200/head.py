@@ -292,7 +292,8 @@ class Os2dAlignment(nn.Module):
         NB, P, H, W = params.shape
         lib = _cabi.load()
         grids = torch.empty(NB, H, W, GRID, GRID, 2, dtype=torch.float32, device=params.device)
-        _cabi.check(lib.os2d_affine_grids(_cabi.ptr(params.contiguous()), NB, P, H, W, 1 if self.use_inverse_geom_model else 0,
+        params = params.contiguous()
+        _cabi.check(lib.os2d_affine_grids(_cabi.ptr(params), NB, P, H, W, 1 if self.use_inverse_geom_model else 0,
                                           _cabi.ptr(grids), _cabi.stream_ptr()), "os2d_affine_grids")
         return grids
 

@@ -255,9 +255,81 @@ def make_singular_theta_golden():
     print("singular theta golden:", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
 
 
+def voc_inputs(seed, n_images=14, n_labels=9, quant=0):
+    """Seeded detections / ground truth per image: (pred boxes, labels, scores, pred image size, gt boxes, labels,
+    difficult, gt image size).  Label 3 never has ground truth, label 6 is never detected, image 2 has no detections,
+    image 5 no ground truth; every third image predicts at another resolution (exercises BoxList.resize).
+    quant > 0 quantises the scores (ties)."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for i in range(n_images):
+        W, H = 640 + 32 * (i % 3), 480 + 16 * (i % 4)
+        ng = 0 if i == 5 else int(torch.randint(1, 9, (1,), generator=g))
+        gxy = torch.rand(ng, 2, generator=g) * torch.tensor([W - 160.0, H - 120.0])
+        gwh = 30 + torch.rand(ng, 2, generator=g) * 120
+        gt = torch.cat([gxy, gxy + gwh], 1)
+        gl = torch.randint(0, n_labels, (ng,), generator=g)
+        gl[gl == 3] = 4
+        gd = (torch.rand(ng, generator=g) < 0.25).to(torch.int64)
+        nd = 0 if i == 2 else int(torch.randint(5, 60, (1,), generator=g))
+        # half of the detections are jittered copies of ground-truth boxes (several per box: duplicates), half random
+        src = torch.randint(0, max(ng, 1), (nd,), generator=g)
+        jit = (torch.rand(nd, 4, generator=g) - 0.5) * 40
+        near = (gt[src] + jit) if ng > 0 else torch.zeros(nd, 4)
+        rxy = torch.rand(nd, 2, generator=g) * torch.tensor([W - 100.0, H - 100.0])
+        rnd = torch.cat([rxy, rxy + 20 + torch.rand(nd, 2, generator=g) * 150], 1)
+        use_near = (torch.rand(nd, generator=g) < 0.6) & (ng > 0)
+        pb = torch.where(use_near[:, None], near, rnd)
+        pb = torch.stack([torch.minimum(pb[:, 0], pb[:, 2]), torch.minimum(pb[:, 1], pb[:, 3]),
+                          torch.maximum(pb[:, 0], pb[:, 2]), torch.maximum(pb[:, 1], pb[:, 3])], 1)
+        pl = torch.where(use_near & (torch.rand(nd, generator=g) < 0.8), gl[src] if ng > 0 else torch.zeros(nd, dtype=torch.int64),
+                         torch.randint(0, n_labels, (nd,), generator=g))
+        pl[pl == 6] = 7
+        ps = torch.rand(nd, generator=g)
+        if quant:
+            ps = (ps * quant).floor() / quant
+        sx = 0.5 if i % 3 == 1 else 1.0             # predictions made on a smaller image: equal ratios (one multiply in
+        sy = (0.5 if i % 2 else 0.25) if i % 3 == 1 else 1.0   # BoxList.resize) or different ratios (per-axis branch)
+        psize = (int(W * sx), int(H * sy))
+        out.append((pb * torch.tensor([sx, sy, sx, sy]), pl, ps, psize, gt, gl, gd, (W, H)))
+    return out
+
+
+def make_voc_golden():
+    """do_voc_evaluation of the reference (voc_eval.py) on the seeded detections above; distinct scores and tied scores,
+    IoU thresholds 0.5 and 0.3 (fp32 comparison), both AP definitions."""
+    from os2d.data.voc_eval import do_voc_evaluation
+    out = {}
+    for tag, seed, quant in (("distinct", 91, 0), ("ties", 92, 16)):
+        data = voc_inputs(seed, quant=quant)
+        preds, gts = [], []
+        for (pb, pl, ps, psize, gt, gl, gd, gsize) in data:
+            b = BoxList(pb, FeatureMapSize(w=psize[0], h=psize[1]), mode="xyxy")
+            b.add_field("labels", pl)
+            b.add_field("scores", ps)
+            preds.append(b)
+            t = BoxList(gt, FeatureMapSize(w=gsize[0], h=gsize[1]), mode="xyxy")
+            t.add_field("labels", gl)
+            t.add_field("difficult", gd)
+            gts.append(t)
+        for thr in (0.5, 0.3):
+            for m07 in (False, True):
+                r = do_voc_evaluation(preds, gts, iou_thresh=thr, use_07_metric=m07)
+                key = "{}_thr{}_{}".format(tag, int(thr * 10), "07" if m07 else "area")
+                for k in ("ap_per_class", "recall_per_class", "n_pos"):
+                    out[key + "_" + k] = np.asarray(r[k], dtype=np.float64)
+                out[key + "_scalars"] = np.array([r["map"], r["map_weighted"], r["recall"], r["ap_joint_classes"]], dtype=np.float64)
+                if not m07 and thr == 0.5:
+                    out[key + "_prec4"] = np.asarray(r["prec"][4], dtype=np.float64)
+                    out[key + "_rec4"] = np.asarray(r["rec"][4], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "voc_eval.npz"), **out)
+    print("voc golden:", {k: out[k].tolist() for k in out if k.endswith("thr5_area_scalars")})
+
+
 if __name__ == "__main__":
     make_head_goldens()
     make_decode_golden()
     make_nms_golden()
     make_eval_iterator_golden()
     make_singular_theta_golden()
+    make_voc_golden()

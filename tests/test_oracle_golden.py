@@ -122,3 +122,35 @@ def _plain_inverse(p, simple):
     det = a * d - b * c
     ia, ib, ic, id_ = d / det, -b / det, -c / det, a / det
     return ia, ib, -(ia * tx + ib * ty), ic, id_, -(ic * tx + id_ * ty)
+
+
+def _voc_arrays(data):
+    """voc_eval.py:28-31: predictions are resized to the ground-truth image size first (BoxList.resize,
+    bounding_box.py:138-163: one fp32 multiply when both ratios agree, per axis otherwise)."""
+    pb, pl, ps, gb, gl, gd = [], [], [], [], [], []
+    for (b, l, s, psize, gt, gtl, gtd, gsize) in data:
+        rw, rh = float(gsize[0]) / psize[0], float(gsize[1]) / psize[1]
+        scaled = b * rw if rw == rh else b * torch.tensor([rw, rh, rw, rh], dtype=torch.float32)
+        pb.append(scaled.numpy()); pl.append(l.numpy()); ps.append(s.numpy())
+        gb.append(gt.numpy()); gl.append(gtl.numpy()); gd.append(gtd.numpy())
+    return pb, pl, ps, gb, gl, gd
+
+
+@pytest.mark.parametrize("tag,seed,quant", [("distinct", 91, 0), ("ties", 92, 16)])
+def test_voc_oracle_matches_reference_golden(tag, seed, quant):
+    from oracle import voc_oracle as vo
+    from _util import voc_inputs
+    gold = np.load(os.path.join(GOLDEN, "voc_eval.npz"))
+    arrays = _voc_arrays(voc_inputs(seed, quant=quant))
+    for thr in (0.5, 0.3):
+        for m07 in (False, True):
+            r = vo.eval_detection_voc(*arrays, iou_thresh=thr, use_07_metric=m07)
+            key = "{}_thr{}_{}".format(tag, int(thr * 10), "07" if m07 else "area")
+            np.testing.assert_array_equal(r["n_pos"], gold[key + "_n_pos"])
+            np.testing.assert_allclose(r["ap_per_class"], gold[key + "_ap_per_class"], rtol=0, atol=1e-12, equal_nan=True)
+            np.testing.assert_allclose(r["recall_per_class"], gold[key + "_recall_per_class"], rtol=0, atol=1e-12, equal_nan=True)
+            np.testing.assert_allclose([r["map"], r["map_weighted"], r["recall"], r["ap_joint_classes"]], gold[key + "_scalars"],
+                                       rtol=0, atol=1e-12)
+            if not m07 and thr == 0.5:
+                np.testing.assert_allclose(r["prec"][4], gold[key + "_prec4"], rtol=0, atol=1e-15, equal_nan=True)
+                np.testing.assert_allclose(r["rec"][4], gold[key + "_rec4"], rtol=0, atol=1e-15)
