@@ -4,7 +4,8 @@
 
 `os2d/modeling/model.py:19` binds ``build_os2d_head_creator`` by name at import time and `model.py:35` constructs
 ``Os2dBoxCoder``; ``install()`` rebinds those names (and the head classes in ``os2d.modeling.head``) to the B200
-implementations and replaces ``Os2dBoxCoder.decode_pyramid`` by an adapter around ``os2d_b200.box_coder``.  The
+implementations, replaces ``Os2dBoxCoder.decode_pyramid`` by an adapter around ``os2d_b200.box_coder`` and
+``os2d.data.voc_eval.do_voc_evaluation`` by the on-device evaluation.  The
 reference's own value types (FeatureMapSize, BoxList) are used inside this package afterwards so that objects crossing
 the boundary in either direction compare equal.  ``main.py``, ``config.py`` and ``evaluate.py`` stay byte-identical.
 See INTEGRATION.md for the launcher one-liner.
@@ -63,11 +64,17 @@ def install(reference_package="os2d"):
     ref_bb.nms = _bc.nms
     ref_bc.nms = _bc.nms
 
-    # 4. batched-class evaluation iterator (evaluate.py:177; needs matplotlib/yacs importable, so only when it imports)
+    # 4. detection evaluation on the device (voc_eval.py:14; evaluate.py:154 binds the name at import)
+    from . import voc_eval as _voc
+    ref_voc = importlib.import_module(reference_package + ".data.voc_eval")
+    ref_voc.do_voc_evaluation = _voc.do_voc_evaluation
+
+    # 5. batched-class evaluation iterator (evaluate.py:177; needs matplotlib/yacs importable, so only when it imports)
     try:
         ref_eval = importlib.import_module(reference_package + ".engine.evaluate")
         from . import evaluate as _ev
         ref_eval.make_iterator_extract_scores_from_images_batched = _ev.make_iterator_extract_scores_from_images_batched
+        ref_eval.do_voc_evaluation = _voc.do_voc_evaluation
     except Exception:   # noqa: BLE001  - the reference's eval module is not importable without matplotlib / yacs
         pass
     _installed = True

@@ -37,6 +37,8 @@ try:
     raise SystemExit("decode on CPU tensors must fail loudly")
 except RuntimeError as e:
     assert "CUDA" in str(e)
+import os2d.data.voc_eval as ref_voc, os2d_b200.voc_eval as bv
+assert ref_voc.do_voc_evaluation is bv.do_voc_evaluation
 print("INSTALL_OK")
 """
 
