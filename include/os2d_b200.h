@@ -108,6 +108,16 @@ int os2d_decode_boxes(int C, int N, int fm_w, float stride_w, float stride_h, fl
 int os2d_nms_segments(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int num_segs,
                       double iou_threshold, uint8_t* keep, void* stream);
 
+/* ---- image pyramid level: PIL Image.resize(BILINEAR) + ToTensor + Normalize (transforms.py:72, dataloader.py:322-341) ----
+ *   img_hwc [H,W,3] uint8 (device) -> out_chw [3,out_h,out_w] fp32 = (resized byte / 255 - mean) / std, bit-identical to
+ *   Pillow's ImagingResample (horizontal pass, uint8 intermediate `tmp` [H,out_w,3], vertical pass; 22-bit fixed point).
+ *   xbounds [out_w,2] / ybounds [out_h,2] = (first tap, tap count), xcoeffs [out_w,xksize] / ycoeffs [out_h,yksize] int32
+ *   (device), computed like Pillow's precompute_coeffs (os2d_b200/pyramid.py); mean3 / std3: 3 HOST floats each;
+ *   out_u8_hwc (optional, may be NULL): the resized bytes [out_h,out_w,3]. */
+int os2d_resize_level(const uint8_t* img_hwc, int H, int W, int out_h, int out_w, const int* xbounds, const int* xcoeffs,
+                      int xksize, const int* ybounds, const int* ycoeffs, int yksize, const float* mean3, const float* std3,
+                      uint8_t* tmp, float* out_chw, uint8_t* out_u8_hwc, void* stream);
+
 /* ---- detection evaluation: matching step of calc_detection_voc_prec_rec (os2d/data/voc_eval.py:109-126) ----
  *   det_boxes [n_det,4] xyxy fp32 (already resized to the ground-truth image size), det_img / det_label [n_det] int32;
  *   ground truth concatenated image by image: gt_boxes [n_gt,4], gt_label [n_gt], gt_offsets [n_images+1];

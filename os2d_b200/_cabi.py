@@ -40,6 +40,8 @@ SIGNATURES = {
     "os2d_decode_boxes": (_c_int, [_c_int, _c_int, _c_int, _c_float, _c_float, _c_float, _c_float, _c_float, _c_float,
                                    _c_float, _c_float, _c_float, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                    _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "os2d_resize_level": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p,
+                                   _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "os2d_voc_match": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_float,
                                 _c_void_p, _c_void_p]),
     "os2d_nms_segments": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, ctypes.c_double, _c_void_p, _c_void_p]),

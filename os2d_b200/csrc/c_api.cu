@@ -176,4 +176,12 @@ int os2d_voc_match(const float* det_boxes, const int* det_img, const int* det_la
                           static_cast<cudaStream_t>(stream));
 }
 
+int os2d_resize_level(const uint8_t* img_hwc, int H, int W, int out_h, int out_w, const int* xbounds, const int* xcoeffs,
+                      int xksize, const int* ybounds, const int* ycoeffs, int yksize, const float* mean3, const float* std3,
+                      uint8_t* tmp, float* out_chw, uint8_t* out_u8_hwc, void* stream) {
+  if (!img_hwc || !xbounds || !xcoeffs || !ybounds || !ycoeffs || !mean3 || !std3 || !tmp || !out_chw) return kErrBadArg;
+  return launch_resize_level(img_hwc, H, W, out_h, out_w, xbounds, xcoeffs, xksize, ybounds, ycoeffs, yksize, mean3, std3, tmp,
+                             out_chw, out_u8_hwc, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -70,6 +70,11 @@ int launch_decode(const DecodeArgs& A, const float* loc, const float* score, con
 int launch_nms(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int num_segs, double iou_thr,
                uint8_t* keep, cudaStream_t st);
 
+// image pyramid level (pyramid.cu): Pillow-exact bilinear resize + ToTensor + Normalize
+int launch_resize_level(const uint8_t* img, int H, int W, int out_h, int out_w, const int* xbounds, const int* xcoeffs, int xk,
+                        const int* ybounds, const int* ycoeffs, int yk, const float* mean, const float* stdv, uint8_t* tmp,
+                        float* out, uint8_t* out_u8, cudaStream_t st);
+
 // detection evaluation (voc.cu)
 int launch_voc_match(const float* det_boxes, const int* det_img, const int* det_label, const float* gt_boxes,
                      const int* gt_label, const int* gt_offsets, int n_det, float iou_thr, int* gt_index, cudaStream_t st);
