@@ -1,6 +1,8 @@
 """In-process A/B timing of two builds of the library (box-to-box and run-to-run variance is a few %, so variants are
 compared interleaved in ONE process on the same buffers): A = os2d_b200/libos2d_b200_base.so (tools/build_baseline_lib.sh),
-B = os2d_b200/libos2d_b200.so.   python tools/gpu_ab.py [rounds=6] [steps=20]"""
+B = os2d_b200/libos2d_b200.so.   python tools/gpu_ab.py [rounds=6] [steps=20] [ENV=VALUE for B only ...]
+Environment switches that a library reads once (static getenv) can be given for B only: they are set while B makes its
+first calls and unset while A does, e.g. `python tools/gpu_ab.py 6 20 OS2D_B200_CONV3_V2=1` with two copies of one build."""
 import ctypes
 import os
 import sys
@@ -16,6 +18,7 @@ from oracle import head_oracle as ho
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+ENV_B = dict(a.split("=", 1) for a in sys.argv[3:])
 
 
 def open_lib(path):
@@ -35,18 +38,28 @@ g = torch.Generator().manual_seed(0)
 cms = (torch.randn(C, D, 15, 15, generator=g) * 0.5 + 0.2).relu()
 fm = (torch.randn(1, D, side, side, generator=g) * 0.5 + 0.2).relu().to(dev)
 tn = ho.random_transform_net(6, seed=1, spread=0.005)
-hc = bh.build_os2d_head_creator(False, True, True, FeatureMapSize(w=16, h=16), FeatureMapSize(w=16, h=16))
-hc.aligner.parameter_regressor.load_state_dict(dict(tn), strict=False)
-hc.eval()
+heads = {}
 acc = {k: {} for k in libs}
 tot = {k: [] for k in libs}
 outs = {}
 with torch.no_grad():
-    _cabi._lib = libs["A(base)"]
-    head = hc.create_os2d_head([cms[i:i + 1].to(dev) for i in range(C)])
+    for name, lib in libs.items():                       # one head (own packed weights) per library
+        for k, v in ENV_B.items():
+            if name.startswith("B"):
+                os.environ[k] = v
+            else:
+                os.environ.pop(k, None)
+        _cabi._lib = lib
+        hc = bh.build_os2d_head_creator(False, True, True, FeatureMapSize(w=16, h=16), FeatureMapSize(w=16, h=16))
+        hc.aligner.parameter_regressor.load_state_dict(dict(tn), strict=False)
+        hc.eval()
+        heads[name] = hc.create_os2d_head([cms[i:i + 1].to(dev) for i in range(C)])
+        heads[name](fm)                                   # first calls: every static switch of this library is read now
+        torch.cuda.synchronize()
     for r in range(R + 1):
         for name, lib in libs.items():
             _cabi._lib = lib
+            head = heads[name]
             head.profile_events = []
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
