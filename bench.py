@@ -114,6 +114,36 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def seeded_transform_net(out_dim, seed=0, spread=0.02):
+    """Seeded synthetic TransformNet weights with the reference's state-dict keys (conv.0/1/3/4, linear) and a non-identity
+    output; both arms of the bench use this one generator (there are no checkpoints offline)."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    tn = {}
+
+    def conv(name, co, ci, k):
+        bound = 1.0 / math.sqrt(ci * k * k)
+        tn[name + ".weight"] = (torch.rand(co, ci, k, k, generator=g) * 2 - 1) * bound
+        tn[name + ".bias"] = (torch.rand(co, generator=g) * 2 - 1) * bound
+
+    def bn(name, c):
+        tn[name + ".weight"] = 0.5 + torch.rand(c, generator=g)
+        tn[name + ".bias"] = 0.1 * torch.randn(c, generator=g)
+        tn[name + ".running_mean"] = 0.05 * torch.randn(c, generator=g)
+        tn[name + ".running_var"] = 0.01 + 0.05 * torch.rand(c, generator=g)
+
+    conv("conv.0", 128, 225, 7)
+    bn("conv.1", 128)
+    conv("conv.3", 64, 128, 5)
+    bn("conv.4", 64)
+    tn["linear.weight"] = spread * torch.randn(out_dim, 64, 5, 5, generator=g)
+    bias = torch.zeros(out_dim)
+    bias[0] = 1
+    bias[4 if out_dim == 6 else 2] = 1
+    tn["linear.bias"] = bias
+    return tn
+
+
 # reference arm / cpu baseline: the oracle port of the reference's CPU implementation, all host threads
 # ---------------------------------------------------------------------------------------------------------------
 def cpu_reference_rate(args, steps, warmup, sample_classes):
@@ -124,7 +154,7 @@ def cpu_reference_rate(args, steps, warmup, sample_classes):
     fm = -(-args.size // 16)
     cms = [(torch.randn(1, D, 15, 15, generator=g) * 0.5 + 0.2).relu() for _ in range(sample_classes)]
     fmap = (torch.randn(args.batch, D, fm, fm, generator=g) * 0.5 + 0.2).relu()
-    tn = ho.random_transform_net(6, seed=1, spread=0.005)
+    tn = seeded_transform_net(6, seed=1, spread=0.005)
     cf = ho.prepare_class_features(cms)
     ncpu = os.cpu_count() or 1
 
@@ -180,7 +210,6 @@ def run_ours(args):
     from os2d_b200 import head as bh
     from os2d_b200 import dist as bd
     from os2d_b200.structures import FeatureMapSize
-    from oracle import head_oracle as ho   # only for the seeded TransformNet weights and the cpu_baseline leg
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -195,7 +224,7 @@ def run_ours(args):
     N = fm_side * fm_side
     B, C = args.batch, args.classes
     cms, fmap = synth(args, dev, seed=1234 + rank)
-    tn = ho.random_transform_net(6, seed=1, spread=0.005)
+    tn = seeded_transform_net(6, seed=1, spread=0.005)
     hc = bh.build_os2d_head_creator(False, True, True, FeatureMapSize(w=16, h=16), FeatureMapSize(w=16, h=16))
     hc.aligner.parameter_regressor.load_state_dict(dict(tn), strict=False)
     hc.eval()

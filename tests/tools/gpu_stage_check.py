@@ -1,6 +1,6 @@
 """Stage-by-stage numerical check of the CUDA kernels against torch ops on the same GPU (diagnostics tool).
 
-    python tools/gpu_stage_check.py <stage> [H W C B]
+    python tests/tools/gpu_stage_check.py <stage> [H W C B]
 stages: env pack corr conv1 conv2 conv3 resample head decode all
 Each stage prints max abs / rel errors; exit code 1 if a stage is out of tolerance.
 Run every stage under `timeout` (a wrong barrier protocol hangs rather than fails).
@@ -9,7 +9,7 @@ import sys
 import os
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))   # repository root
 import torch
 import torch.nn.functional as F
 

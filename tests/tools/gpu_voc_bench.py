@@ -1,11 +1,11 @@
 """Measurement of the on-device detection evaluation against the numpy restatement of the
-reference's voc_eval.py on the host.   python tools/gpu_voc_bench.py > profiles/r01_voc_eval.json"""
+reference's voc_eval.py on the host.   python tests/tools/gpu_voc_bench.py > profiles/r01_voc_eval.json"""
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch

@@ -14,7 +14,7 @@ import torch
 from os2d_b200 import _cabi
 from os2d_b200 import head as bh
 from os2d_b200.structures import FeatureMapSize
-from oracle import head_oracle as ho
+from _synth import seeded_transform_net
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 20
@@ -37,7 +37,7 @@ dev = torch.device("cuda", 0)
 g = torch.Generator().manual_seed(0)
 cms = (torch.randn(C, D, 15, 15, generator=g) * 0.5 + 0.2).relu()
 fm = (torch.randn(1, D, side, side, generator=g) * 0.5 + 0.2).relu().to(dev)
-tn = ho.random_transform_net(6, seed=1, spread=0.005)
+tn = seeded_transform_net(6, seed=1, spread=0.005)
 heads = {}
 acc = {k: {} for k in libs}
 tot = {k: [] for k in libs}

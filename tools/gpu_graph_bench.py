@@ -9,14 +9,14 @@ import torch
 
 from os2d_b200 import head as bh, GraphedHead
 from os2d_b200.structures import FeatureMapSize
-from oracle import head_oracle as ho
+from _synth import seeded_transform_net
 
 res = {}
 for name, C, side in (("cfg1_512px_c4", 4, 32), ("640px_c16", 16, 40), ("cfg2_1280px_c100", 100, 80)):
     g = torch.Generator().manual_seed(0)
     cms = (torch.randn(C, 1024, 15, 15, generator=g) * 0.5 + 0.2).relu().cuda()
     fm = (torch.randn(1, 1024, side, side, generator=g) * 0.5 + 0.2).relu().cuda()
-    tn = ho.random_transform_net(6, seed=1, spread=0.005)
+    tn = seeded_transform_net(6, seed=1, spread=0.005)
     hc = bh.build_os2d_head_creator(False, True, True, FeatureMapSize(w=16, h=16), FeatureMapSize(w=16, h=16))
     hc.aligner.parameter_regressor.load_state_dict(dict(tn), strict=False)
     hc.eval()

@@ -5,14 +5,14 @@ import torch
 from os2d_b200 import head as bh
 from os2d_b200.structures import FeatureMapSize
 from os2d_b200.box_coder import Os2dBoxCoder
-from oracle import head_oracle as ho
+from _synth import seeded_transform_net
 
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 S = 80
 g = torch.Generator().manual_seed(0)
 cms = (torch.randn(C, 1024, 15, 15, generator=g) * 0.5 + 0.2).relu().cuda()
 fm = (torch.randn(1, 1024, S, S, generator=g) * 0.5 + 0.2).relu().cuda()
-tn = ho.random_transform_net(6, seed=1, spread=0.005)
+tn = seeded_transform_net(6, seed=1, spread=0.005)
 hc = bh.build_os2d_head_creator(False, True, True, FeatureMapSize(w=16, h=16), FeatureMapSize(w=16, h=16))
 hc.aligner.parameter_regressor.load_state_dict(dict(tn), strict=False)
 hc.eval()
