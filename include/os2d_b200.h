@@ -80,6 +80,17 @@ int os2d_resample_boxes(const void* rawvol, const float* params, int planes, int
                         float* corners, long long score_plane_stride, long long loc_plane_stride,
                         long long corners_plane_stride, void* stream);
 
+/* K3 fused with the all-gather of the class-sharded multi-GPU path ("K3's epilogue writes directly
+ * into the rank's slice of the gather buffer ... stretch: P2P"): same computation as os2d_resample_boxes, but the 13 outputs of
+ * every location are stored into the gather buffer of EVERY rank.  peer_bases: DEVICE array of n_peers pointers to the
+ * (peer-mapped, symmetric) fp32 gather buffers; *_off: float offsets of this call's first plane inside a buffer;
+ * plane_stride: floats between consecutive planes (13 * H * W for the [G,B,C/G,13,N] layout).  A cross-rank barrier must
+ * follow before the buffers are read (os2d_b200/dist.py).  Not yet validated on a multi-GPU box. */
+int os2d_resample_boxes_p2p(const void* rawvol, const float* params, int planes, int P, int H, int W, int inverse,
+                            float stride_w, float stride_h, float box_w, float box_h, const void* const* peer_bases, int n_peers,
+                            long long score_off, long long loc_off, long long corners_off, long long plane_stride,
+                            void* stream);
+
 /* ---- secondary entry points: the public methods of the reference classes that take / return the large tensors ----
  * os2d_pack_corr_maps:     fp32 correlation maps [planes,225,H*W] -> zvol / rawvol (TransformationNet.forward input side,
  *                          head.py:648-650); then os2d_transform_conv 1..3 give the parameters.

@@ -33,6 +33,8 @@ SIGNATURES = {
     "os2d_resample_boxes": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float,
                                      _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_ll, _c_ll,
                                      _c_void_p]),
+    "os2d_resample_boxes_p2p": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float,
+                                         _c_float, _c_float, _c_void_p, _c_int, _c_ll, _c_ll, _c_ll, _c_ll, _c_void_p]),
     "os2d_pack_corr_maps": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "os2d_affine_grids": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
     "os2d_resample_with_grid": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p,

@@ -131,6 +131,16 @@ int os2d_resample_boxes(const void* rawvol, const float* params, int planes, int
                          score_plane_stride, loc_plane_stride, corners_plane_stride, static_cast<cudaStream_t>(stream));
 }
 
+int os2d_resample_boxes_p2p(const void* rawvol, const float* params, int planes, int P, int H, int W, int inverse,
+                            float stride_w, float stride_h, float box_w, float box_h, const void* const* peer_bases, int n_peers,
+                            long long score_off, long long loc_off, long long corners_off, long long plane_stride,
+                            void* stream) {
+  if (!rawvol || !params || !peer_bases) return kErrBadArg;
+  return launch_resample_p2p(rawvol, params, planes, P, H, W, inverse, stride_w, stride_h, box_w, box_h,
+                             reinterpret_cast<float* const*>(const_cast<void* const*>(peer_bases)), n_peers, score_off, loc_off,
+                             corners_off, plane_stride, static_cast<cudaStream_t>(stream));
+}
+
 int os2d_pack_corr_maps(const float* corr, int planes, int H, int W, void* zvol, void* rawvol, void* stream) {
   if (!corr || !zvol || !rawvol) return kErrBadArg;
   return launch_pack_corr(corr, planes, H * W, zvol, rawvol, static_cast<cudaStream_t>(stream));

@@ -50,6 +50,11 @@ int launch_resample(const void* rawvol, const float* params, int planes, int P, 
                     float stride_w, float stride_h, float box_w, float box_h, float* score, float* loc,
                     float* corners, long long score_ps, long long loc_ps, long long corners_ps, cudaStream_t st);
 
+// K3 with the all-gather fused in: outputs stored into every rank's gather buffer through peer pointers (resample_p2p.cu)
+int launch_resample_p2p(const void* rawvol, const float* params, int planes, int P, int H, int W, int inverse,
+                        float stride_w, float stride_h, float box_w, float box_h, float* const* peers, int n_peers,
+                        long long score_off, long long loc_off, long long corners_off, long long plane_stride, cudaStream_t st);
+
 // secondary entry points (aux.cu): stand-alone TransformationNet / Os2dAlignment / resample_of_correlation_map_* methods
 int launch_pack_corr(const float* corr, int planes, int N, void* zvol, void* rawvol, cudaStream_t st);
 int launch_affine_grids(const float* params, int planes, int P, int N, int inverse, float* grid, cudaStream_t st);

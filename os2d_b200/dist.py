@@ -58,14 +58,41 @@ def unpack_gathered(buffer, num_classes):
     return full[:, :, 1:5], full[:, :, 0], full[:, :, 5:13]
 
 
+class SymmetricGatherBuffer:
+    """[world, B, per, 13, N] gather buffer in symmetric memory (torch.distributed._symmetric_memory): every rank maps the
+    buffers of all ranks, so K3 can store its outputs into all of them (csrc/resample_p2p.cu) and a device-side barrier
+    replaces the all-gather.  NOT yet validated on a multi-GPU box; ``ClassShardedHead(fused_gather=True)`` opts in."""
+
+    def __init__(self, B, num_classes, N, world_size, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.per = padded_block(num_classes, world_size)
+        self.shape = (world_size, B, self.per, OUT_PLANES, N)
+        self.buffer = symm_mem.empty(*self.shape, dtype=torch.float32, device=device)
+        self.buffer.zero_()
+        self.handle = symm_mem.rendezvous(self.buffer, group if group is not None else dist.group.WORLD)
+        self.ptrs = torch.tensor(list(self.handle.buffer_ptrs), dtype=torch.int64, device=device)
+        self.slice_elems = B * self.per * OUT_PLANES * N
+
+    def out_peers(self, rank):
+        return self.ptrs, rank * self.slice_elems, self.per
+
+    def barrier(self):
+        """All ranks have finished their K3 stores (stream-ordered, system-scope release / acquire)."""
+        self.handle.barrier()
+
+
 class ClassShardedHead:
     """Runs an ``Os2dHead`` built from this rank's class block and all-gathers the per-class outputs.
 
     ``head_factory(class_maps_block)`` creates the local head (normally
     ``os2d_head_creator.create_os2d_head``); it is only called when the block is not empty.
+    ``fused_gather=True`` (experimental): the head's K3 writes into every rank's symmetric gather buffer itself and a
+    device-side barrier replaces the NCCL all-gather.
     """
 
-    def __init__(self, class_feature_maps, head_factory, group=None):
+    def __init__(self, class_feature_maps, head_factory, group=None, fused_gather=False):
+        self.fused_gather = bool(fused_gather)
+        self._symm = {}
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -77,6 +104,8 @@ class ClassShardedHead:
     def forward(self, feature_maps):
         B, _, H, W = feature_maps.shape
         N = H * W
+        if self.fused_gather and self.world > 1:
+            return self._forward_fused(feature_maps, B, H, W, N)
         buf = allocate_gather_buffer(B, self.num_classes, N, self.world, feature_maps.device)
         if self.head is not None:
             s_v, l_v, c_v = local_views(buf, self.rank)
@@ -94,5 +123,19 @@ class ClassShardedHead:
         loc, score, corners = unpack_gathered(buf, self.num_classes)
         return (loc.reshape(B, self.num_classes, 4, H, W), score.reshape(B, self.num_classes, 1, H, W),
                 corners.reshape(B, self.num_classes, 8, H, W))
+
+    def _forward_fused(self, feature_maps, B, H, W, N):
+        key = (B, N)
+        sg = self._symm.get(key)
+        if sg is None:                                   # collective allocation + rendezvous, once per shape
+            sg = self._symm[key] = SymmetricGatherBuffer(B, self.num_classes, N, self.world, feature_maps.device, self.group)
+        sg.barrier()                                     # every rank is done reading the previous contents
+        if self.head is not None:
+            self.head(feature_maps, out_peers=sg.out_peers(self.rank))
+        sg.barrier()                                     # every rank's stores have landed everywhere
+        loc, score, corners = unpack_gathered(sg.buffer, self.num_classes)
+        # the buffer is reused by the next call: hand out copies (the reference API returns fresh tensors)
+        return (loc.reshape(B, self.num_classes, 4, H, W).clone(), score.reshape(B, self.num_classes, 1, H, W).clone(),
+                corners.reshape(B, self.num_classes, 8, H, W).clone())
 
     __call__ = forward

@@ -433,10 +433,14 @@ class Os2dHead(nn.Module):
         self.profile_events.append((name, e0, e1))
         return rc
 
-    def forward(self, feature_maps, out_views=None):
+    def forward(self, feature_maps, out_views=None, out_peers=None):
         """feature_maps [B,D,H,W] -> (loc [B,C,4,H,W], rec [B,C,1,H,W], rec_transform_detached (same tensor under
         no-grad, head.py:400-402), corners [B,C,8,H,W]).  ``out_views`` (extension, default None): (score, loc, corners)
-        strided views [B,C,k,H*W] to write into instead of fresh tensors; the call then returns None."""
+        strided views [B,C,k,H*W] to write into instead of fresh tensors; the call then returns None.
+        ``out_peers`` (extension, multi-GPU): ``(ptrs, slice_offset, per)`` - int64 CUDA tensor of the base pointers of every
+        rank's [G,B,per,13,N] gather buffer (peer-mapped), the float offset of THIS rank's slice in such a buffer and the
+        number of class slots per rank; K3 then stores its outputs into all those buffers itself (csrc/resample_p2p.cu)
+        and the call returns None - the caller synchronises the ranks before reading."""
         if torch.is_grad_enabled() and (feature_maps.requires_grad or
                                         any(p.requires_grad for p in self.aligner.parameters())):
             raise RuntimeError("os2d_b200.Os2dHead implements inference only; call it under torch.no_grad() "
@@ -464,7 +468,10 @@ class Os2dHead(nn.Module):
         _cabi.check(self._timed("pack_image", lib.os2d_pack_image_features, _cabi.ptr(fm), B, D, N, _cabi.ptr(inv_ws),
                                 _cabi.ptr(img_packed), st), "os2d_pack_image_features")
 
-        if out_views is None:
+        if out_peers is not None:
+            assert out_views is None, "out_views and out_peers are exclusive"
+            loc = score = corners = o_score = o_loc = o_corners = None
+        elif out_views is None:
             loc = torch.empty(B, C, 4, H, W, dtype=torch.float32, device=dev)
             score = torch.empty(B, C, 1, H, W, dtype=torch.float32, device=dev)
             corners = torch.empty(B, C, 8, H, W, dtype=torch.float32, device=dev)
@@ -487,6 +494,17 @@ class Os2dHead(nn.Module):
             _cabi.check(self._timed("corr", lib.os2d_correlate, _cabi.ptr(img_packed), _cabi.ptr(cls), B, cc, D, H, W,
                                     _cabi.ptr(zvol), _cabi.ptr(rawvol), st), "os2d_correlate")
             params = run_transform_convs(pw, P, zvol, planes, H, W, timed=self._timed)
+            if out_peers is not None:
+                # K3 + collective in one kernel: outputs go to this rank's slice of every rank's gather buffer
+                ptrs, slice_off, per = out_peers
+                for b in range(B):
+                    base = int(slice_off) + (b * int(per) + c0) * 13 * N
+                    _cabi.check(self._timed("resample", lib.os2d_resample_boxes_p2p, _cabi.ptr(rawvol[b * cc:]),
+                                            _cabi.ptr(params[b * cc:]), cc, P, H, W, inverse, float(gen.box_stride.w),
+                                            float(gen.box_stride.h), float(gen.box_size.w), float(gen.box_size.h),
+                                            _cabi.ptr(ptrs), int(ptrs.numel()), base, base + N, base + 5 * N, 13 * N, st),
+                                "os2d_resample_boxes_p2p")
+                continue
             # K3 writes straight into the final tensors (or into caller-provided views, e.g. this rank's slice of the
             # all-gather buffer): one launch when the planes of this chunk are contiguous in the output, else one per image
             if cc == C and out_views is None:
@@ -500,7 +518,7 @@ class Os2dHead(nn.Module):
                                         ctypes.c_void_p(o_score[b0, c0].data_ptr()), ctypes.c_void_p(o_loc[b0, c0].data_ptr()),
                                         ctypes.c_void_p(o_corners[b0, c0].data_ptr()), o_score.stride(1), o_loc.stride(1),
                                         o_corners.stride(1), st), "os2d_resample_boxes")
-        if out_views is not None:
+        if out_views is not None or out_peers is not None:
             return None
         return loc, score, score, corners
 

@@ -8,7 +8,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, fused=False):
     import torch.distributed as dist
     from os2d_b200 import head as bh, dist as bd
     from os2d_b200.structures import FeatureMapSize
@@ -25,8 +25,10 @@ def _worker(rank, world, port, ret):
     hc.eval()
     with torch.no_grad():
         maps = [c.cuda() for c in cms]
-        sharded = bd.ClassShardedHead(maps, hc.create_os2d_head)
+        sharded = bd.ClassShardedHead(maps, hc.create_os2d_head, fused_gather=fused)
         loc, score, corners = sharded(fm.cuda())
+        if fused:                                   # second call: buffer reuse + the leading barrier
+            loc, score, corners = sharded(fm.cuda())
         full = hc.create_os2d_head(maps)
         rloc, rscore, _, rcorners = full(fm.cuda())
     torch.cuda.synchronize()
@@ -41,4 +43,16 @@ def test_class_sharded_head_equals_single_gpu():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2 or not os.environ.get("OS2D_B200_TEST_FUSED_GATHER"),
+                    reason="needs 2 GPUs; the K3 + peer-store path is experimental (set OS2D_B200_TEST_FUSED_GATHER=1, run under timeout)")
+def test_fused_gather_equals_single_gpu():
+    """K3 storing into every rank's symmetric gather buffer (csrc/resample_p2p.cu) + device-side barrier == single GPU."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret, True), nprocs=2, join=True)
     assert ret[0] and ret[1]
