@@ -36,6 +36,9 @@ int os2d_b200_abi_version(void);
 const char* os2d_b200_last_error(void);
 /* number of SMs of the current device (persistent-grid size) */
 int os2d_b200_num_sms(void);
+/* number of kernels this library has launched in this process so far (every launcher counts; bench.py reports the delta over
+ * its timed region as `gpu_launches`) */
+unsigned long long os2d_b200_launch_count(void);
 
 /* ---- K0: operand preparation -------------------------------------------------------------------------
  * Class side (head.py:241-259 resize to 15x15, :293 L2 norm, :342-344 transposed channel order):
@@ -85,7 +88,8 @@ int os2d_resample_boxes(const void* rawvol, const float* params, int planes, int
  * every location are stored into the gather buffer of EVERY rank.  peer_bases: DEVICE array of n_peers pointers to the
  * (peer-mapped, symmetric) fp32 gather buffers; *_off: float offsets of this call's first plane inside a buffer;
  * plane_stride: floats between consecutive planes (13 * H * W for the [G,B,C/G,13,N] layout).  A cross-rank barrier must
- * follow before the buffers are read (os2d_b200/dist.py).  Not yet validated on a multi-GPU box. */
+ * follow before the buffers are read (os2d_b200/dist.py).  Same kernel as os2d_resample_boxes, instantiated with a peer
+ * sink (csrc/resample.cu); validated on 2 and 8 GPUs (tests/test_gpu_dist.py). */
 int os2d_resample_boxes_p2p(const void* rawvol, const float* params, int planes, int P, int H, int W, int inverse,
                             float stride_w, float stride_h, float box_w, float box_h, const void* const* peer_bases, int n_peers,
                             long long score_off, long long loc_off, long long corners_off, long long plane_stride,
@@ -118,6 +122,38 @@ int os2d_decode_boxes(int C, int N, int fm_w, float stride_w, float stride_h, fl
  *   seg_offsets [num_segs+1]; every segment <= 10000 boxes; keep [total] (1 = survives) in `order` positions. */
 int os2d_nms_segments(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int num_segs,
                       double iou_threshold, uint8_t* keep, void* stream);
+
+/* ---- K4+K5 fused: decode_pyramid in two launches (box_coder.py:448-536, :424-437; bounding_box.py:344-387) -----------
+ * os2d_detect_pyramid: ONE launch, one CTA per real label: decode (torchvision BoxCoder.decode_single, clip, empty / score
+ *   filter, BoxList.resize to the original image), candidate list in the reference's concatenation order (class view,
+ *   level, anchor), NMS in consecutive chunks of 10000 iterated to the fixpoint, final score-descending order.
+ *   levels: HOST array of num_levels (<= 12) descriptors with DEVICE tensors; views of label i are
+ *   view_ids[view_offsets[i] .. view_offsets[i+1]) (device int32 arrays; duplicated class ids merge, box_coder.py:483-488).
+ *   Candidates / results are flat indices f = C * sum_{k<l} N_k + view * N_l + anchor.
+ *   Workspaces (device): cand_ws, out_ids int32 [C * sum_l N_l]; key_ws uint64 [C * sum_l N_l], may be NULL when no label
+ *   can exceed one chunk (max_views_per_label * sum_l N_l <= 10000); counts [n_labels]; offsets [n_labels + 1] (exclusive scan
+ *   of counts, offsets[n_labels] = number of detections); done_counter: one zero-initialised uint32, reset by the kernel.
+ * os2d_gather_detections: second launch, writes the detections label by label (label order = order of view_offsets),
+ *   score-descending inside a label: boxes [T,4], scores [T], labels [T] int64 (= label_values[label]), anchors [T,4]
+ *   ("default_boxes"), corners [T,8] (or NULL), T = offsets[n_labels] read back by the caller between the two launches. */
+typedef struct os2d_pyramid_level {
+  const float* loc;      /* [C,4,N] */
+  const float* score;    /* [C,N] */
+  const float* corners;  /* [C,8,N] or NULL */
+  int num_anchors;       /* N = fm_h * fm_w */
+  int fm_w;
+  float img_w, img_h;    /* clip window: image size of this pyramid level */
+  float scale_x, scale_y;/* level -> original image (BoxList.resize), 1 without inverse transforms */
+  int same_scale;        /* ratio_w == ratio_h branch of BoxList.resize: single multiply by scale_x */
+} os2d_pyramid_level;
+int os2d_detect_pyramid(const os2d_pyramid_level* levels, int num_levels, int num_views, const int32_t* view_offsets,
+                        const int32_t* view_ids, int n_labels, int max_views_per_label, float stride_w, float stride_h,
+                        float box_w, float box_h, float score_thr, double iou_threshold, int32_t* cand_ws, uint64_t* key_ws, int32_t* out_ids,
+                        int32_t* counts, int32_t* offsets, uint32_t* done_counter, void* stream);
+int os2d_gather_detections(const os2d_pyramid_level* levels, int num_levels, int num_views, const int32_t* view_offsets,
+                           int n_labels, float stride_w, float stride_h, float box_w, float box_h, const int32_t* out_ids,
+                           const int32_t* counts, const int32_t* offsets, const int64_t* label_values, float* boxes,
+                           float* scores, int64_t* labels, float* anchors, float* corners, void* stream);
 
 /* ---- image pyramid level: PIL Image.resize(BILINEAR) + ToTensor + Normalize (transforms.py:72, dataloader.py:322-341) ----
  *   img_hwc [H,W,3] uint8 (device) -> out_chw [3,out_h,out_w] fp32 = (resized byte / 255 - mean) / std, bit-identical to

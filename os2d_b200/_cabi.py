@@ -4,6 +4,7 @@ There is deliberately no fallback: if the shared library is missing or an entry 
 caller gets an exception.  PyTorch is only used by the callers for device memory and streams.
 """
 import ctypes
+import functools
 import os
 
 _LIB_NAME = "libos2d_b200.so"
@@ -14,11 +15,21 @@ _c_float = ctypes.c_float
 _c_void_p = ctypes.c_void_p
 _c_ll = ctypes.c_longlong
 
+MAX_PYRAMID_LEVELS = 12
+
+
+class PyramidLevel(ctypes.Structure):
+    """os2d_pyramid_level of include/os2d_b200.h"""
+    _fields_ = [("loc", _c_void_p), ("score", _c_void_p), ("corners", _c_void_p), ("num_anchors", _c_int), ("fm_w", _c_int),
+                ("img_w", _c_float), ("img_h", _c_float), ("scale_x", _c_float), ("scale_y", _c_float), ("same_scale", _c_int)]
+
+
 # name -> (restype, argtypes); mirrors include/os2d_b200.h one to one
 SIGNATURES = {
     "os2d_b200_abi_version": (_c_int, []),
     "os2d_b200_last_error": (ctypes.c_char_p, []),
     "os2d_b200_num_sms": (_c_int, []),
+    "os2d_b200_launch_count": (ctypes.c_ulonglong, []),
     "os2d_pack_class_features": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
                                           _c_void_p]),
     "os2d_pack_class_features_ragged": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
@@ -42,6 +53,12 @@ SIGNATURES = {
     "os2d_decode_boxes": (_c_int, [_c_int, _c_int, _c_int, _c_float, _c_float, _c_float, _c_float, _c_float, _c_float,
                                    _c_float, _c_float, _c_float, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                    _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "os2d_detect_pyramid": (_c_int, [ctypes.POINTER(PyramidLevel), _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_float,
+                                     _c_float, _c_float, _c_float, _c_float, ctypes.c_double, _c_void_p, _c_void_p, _c_void_p,
+                                     _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "os2d_gather_detections": (_c_int, [ctypes.POINTER(PyramidLevel), _c_int, _c_int, _c_void_p, _c_int, _c_float, _c_float,
+                                        _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                        _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "os2d_resize_level": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p,
                                    _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "os2d_voc_match": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_float,
@@ -96,5 +113,39 @@ def ptr(t):
 
 
 def stream_ptr():
+    """Current stream of the CURRENT device: entry points run under ``on_device_of`` so this is the tensors' device."""
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _first_cuda_tensor(obj, depth=0):
+    import torch
+    if isinstance(obj, torch.Tensor):
+        return obj if obj.device.type == "cuda" else None
+    if depth < 2 and isinstance(obj, (list, tuple)):
+        for o in obj:
+            t = _first_cuda_tensor(o, depth + 1)
+            if t is not None:
+                return t
+    if hasattr(obj, "bbox_xyxy"):
+        return _first_cuda_tensor(obj.bbox_xyxy, depth + 1)
+    return None
+
+
+def on_device_of(fn):
+    """Decorator of the public entry points: run ``fn`` with the CUDA device of its first CUDA tensor argument current.
+    The C ABI launches on the current device's stream and caches per-device state keyed on the current device, so a call
+    with tensors on cuda:1 while cuda:0 is current must switch first (and switch back afterwards)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        import torch
+        t = None
+        for a in list(args) + list(kwargs.values()):
+            t = _first_cuda_tensor(a)
+            if t is not None:
+                break
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kwargs)
+    return wrapper

@@ -41,6 +41,7 @@ class BoxGridGenerator:
         return self._cache[key]
 
 
+@_cabi.on_device_of
 def nms(boxes, nms_iou_threshold, nms_max_batch=NMS_MAX_BATCH, nms_score_threshold=float("-inf"),
         do_separate_per_label=False):
     """Chunked, iterated greedy NMS with the reference semantics (bounding_box.py:344-387); returns the indices
@@ -210,13 +211,135 @@ class Os2dBoxCoder:
         keep = keep[torch.sort(sc, dim=0, descending=True)[1]]
         return boxes[keep]
 
+    @_cabi.on_device_of
     def decode_pyramid(self, loc_scores_pyramid, cls_scores_pyramid, img_size_pyramid, class_ids,
                        nms_score_threshold=0.0, nms_iou_threshold=0.3, inverse_box_transforms=None,
                        transform_corners_pyramid=None):
         """Same contract as box_coder.py:448-536.  loc [C,4,N_l], cls [C,N_l] (and corners [C,8,N_l]) per level ->
         BoxList with fields scores, labels, default_boxes (, transform_corners).  ``inverse_box_transforms`` may be
-        reference TransformList objects that only resize (their effect is obtained by probing them with a unit
-        box list) or anything with a ``target_size`` / callable returning a resized BoxList."""
+        reference TransformList objects that only resize (their effect is obtained by probing them with a
+        box list) or anything with a ``target_size`` / callable returning a resized BoxList.
+
+        Two launches for any number of classes, levels and candidates (csrc/detect.cu): os2d_detect_pyramid (one CTA per
+        real label: decode, filter, candidate order, chunked NMS to the fixpoint, final order) and
+        os2d_gather_detections; the only host synchronisation is the 4-byte read of the detection count between them."""
+        lib = _cabi.load()
+        num_classes = len(class_ids)
+        device = cls_scores_pyramid[0].device
+        if device.type != "cuda":
+            raise RuntimeError("os2d_b200 requires CUDA tensors (no CPU path)")
+        gen = self.output_box_grid_generator
+        have_corners = transform_corners_pyramid is not None
+        st = _cabi.stream_ptr()
+        L = len(cls_scores_pyramid)
+        if L > _cabi.MAX_PYRAMID_LEVELS:
+            raise NotImplementedError("os2d_detect_pyramid handles up to {} pyramid levels".format(_cabi.MAX_PYRAMID_LEVELS))
+        levels = (_cabi.PyramidLevel * L)()
+        alive = []          # contiguous fp32 copies must outlive the asynchronous launches
+        out_size = None
+        sum_n = 0
+        for i_p, (loc, cls) in enumerate(zip(loc_scores_pyramid, cls_scores_pyramid)):
+            assert cls.device == device and loc.device == device, "scores and boxes should be on the same device"
+            img_size = img_size_pyramid[i_p]
+            fm = self._get_feature_map_size_per_image_size(img_size)
+            N = fm.w * fm.h
+            assert cls.shape == (num_classes, N) and loc.shape == (num_classes, 4, N)
+            if inverse_box_transforms is not None:
+                target = _probe_transform_target(inverse_box_transforms[i_p], img_size)
+                rw, rh = float(target.w) / img_size.w, float(target.h) / img_size.h
+            else:
+                target, rw, rh = img_size, 1.0, 1.0
+            if out_size is None:
+                out_size = target
+            assert target == out_size, "all pyramid levels must map to the same image size (bounding_box.py:403)"
+            loc_c = loc.float().contiguous()
+            cls_c = cls.float().contiguous()
+            cor_c = transform_corners_pyramid[i_p].float().contiguous() if have_corners else None
+            if have_corners:
+                assert cor_c.shape == (num_classes, 8, N)
+            alive += [loc_c, cls_c, cor_c]
+            lv = levels[i_p]
+            lv.loc, lv.score = loc_c.data_ptr(), cls_c.data_ptr()
+            lv.corners = cor_c.data_ptr() if have_corners else None
+            lv.num_anchors, lv.fm_w = N, fm.w
+            lv.img_w, lv.img_h = float(img_size.w), float(img_size.h)
+            lv.scale_x, lv.scale_y, lv.same_scale = rw, rh, 1 if rw == rh else 0
+            sum_n += N
+
+        view_off, view_ids, label_values, n_labels, max_views = self._label_tables(class_ids, device)
+        F = num_classes * sum_n
+        cand = torch.empty(F, dtype=torch.int32, device=device)
+        out_ids = torch.empty(F, dtype=torch.int32, device=device)
+        keys = torch.empty(F, dtype=torch.int64, device=device) if max_views * sum_n > NMS_MAX_BATCH else None
+        counts = torch.empty(n_labels, dtype=torch.int32, device=device)
+        offsets = torch.empty(n_labels + 1, dtype=torch.int32, device=device)
+        done = self._done_counter(device)
+        grid_args = (float(gen.box_stride.w), float(gen.box_stride.h), float(gen.box_size.w), float(gen.box_size.h))
+        rc = lib.os2d_detect_pyramid(levels, L, num_classes, _cabi.ptr(view_off), _cabi.ptr(view_ids), n_labels, max_views,
+                                     *grid_args, float(nms_score_threshold), float(nms_iou_threshold), _cabi.ptr(cand),
+                                     _cabi.ptr(keys), _cabi.ptr(out_ids), _cabi.ptr(counts), _cabi.ptr(offsets),
+                                     _cabi.ptr(done), st)
+        _cabi.check(rc, "os2d_detect_pyramid")
+        total = int(offsets[n_labels].item())                     # the one host synchronisation: number of detections
+        boxes = torch.empty(total, 4, dtype=torch.float32, device=device)
+        scores = torch.empty(total, dtype=torch.float32, device=device)
+        labels = torch.empty(total, dtype=torch.long, device=device)
+        anchors = torch.empty(total, 4, dtype=torch.float32, device=device)
+        corners = torch.empty(total, 8, dtype=torch.float32, device=device) if have_corners else None
+        if total > 0:
+            rc = lib.os2d_gather_detections(levels, L, num_classes, _cabi.ptr(view_off), n_labels, *grid_args,
+                                            _cabi.ptr(out_ids), _cabi.ptr(counts), _cabi.ptr(offsets), _cabi.ptr(label_values),
+                                            _cabi.ptr(boxes), _cabi.ptr(scores), _cabi.ptr(labels), _cabi.ptr(anchors),
+                                            _cabi.ptr(corners), st)
+            _cabi.check(rc, "os2d_gather_detections")
+        cur = torch.cuda.current_stream()
+        for t in alive + [cand, out_ids, keys, counts, offsets]:
+            if t is not None:
+                t.record_stream(cur)
+        out = BoxList(boxes, out_size if out_size is not None else img_size_pyramid[0])
+        out.add_field("scores", scores)
+        out.add_field("default_boxes", BoxList(anchors, out.image_size))
+        out.add_field("labels", labels)
+        if have_corners:
+            out.add_field("transform_corners", corners)
+        if self.do_nms_across_classes and len(out) > 0:
+            out = self._nms_box_lists([out], nms_iou_threshold)
+        return out
+
+    def _label_tables(self, class_ids, device):
+        """Device tables of the label structure, cached per class-id tuple: views of real label i (set order, box_coder.py:483)
+        are view_ids[view_off[i]:view_off[i+1]] in class-view order."""
+        key = (tuple(int(c) for c in class_ids), device.index)
+        cache = self.__dict__.setdefault("_label_cache", {})
+        if key not in cache:
+            label_order = list(set(class_ids))                       # same iteration order as box_coder.py:483
+            views = [[i for i, c in enumerate(class_ids) if c == l] for l in label_order]
+            off = [0]
+            for v in views:
+                off.append(off[-1] + len(v))
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = (torch.tensor(off, dtype=torch.int32).to(device),
+                          torch.tensor([i for v in views for i in v], dtype=torch.int32).to(device),
+                          torch.tensor([int(l) for l in label_order], dtype=torch.long).to(device),
+                          len(label_order), max(len(v) for v in views))
+        return cache[key]
+
+    def _done_counter(self, device):
+        """Zero-initialised completion counter of os2d_detect_pyramid (reset by the kernel), one per device and stream."""
+        key = (device.index, torch.cuda.current_stream().cuda_stream)
+        cache = self.__dict__.setdefault("_done_cache", {})
+        if key not in cache:
+            cache[key] = torch.zeros(1, dtype=torch.int32, device=device)
+        return cache[key]
+
+    @_cabi.on_device_of
+    def decode_pyramid_staged(self, loc_scores_pyramid, cls_scores_pyramid, img_size_pyramid, class_ids,
+                              nms_score_threshold=0.0, nms_iou_threshold=0.3, inverse_box_transforms=None,
+                              transform_corners_pyramid=None):
+        """The staged form of decode_pyramid (round-1 path, kept as the unfused ablation and as an independent check of the
+        fused kernels at sizes the CPU oracle cannot reach): os2d_decode_boxes per level, candidate ordering / sorting with
+        torch index ops, os2d_nms_segments per pass.  Same results bit for bit (tests/test_gpu_postproc.py)."""
         lib = _cabi.load()
         num_classes = len(class_ids)
         device = cls_scores_pyramid[0].device
@@ -368,6 +491,14 @@ def _probe_transform_target(transform, img_size):
     """Image size a box transform maps ``img_size`` boxes to."""
     if hasattr(transform, "target_size"):
         return transform.target_size
-    probe = BoxList(torch.zeros(1, 4), img_size)
-    res = transform(probe)
-    return FeatureMapSize(w=res.image_size.w, h=res.image_size.h)
+    # probe with a non-degenerate box: the decode kernel applies the inverse transform as a per-axis rescale
+    # (BoxList.resize, bounding_box.py:138-163), so anything else (flips, crops) must be refused, not mis-placed
+    box = torch.tensor([[1.0, 2.0, 3.0, 5.0]])
+    res = transform(BoxList(box.clone(), img_size))
+    target = FeatureMapSize(w=res.image_size.w, h=res.image_size.h)
+    rw, rh = float(target.w) / img_size.w, float(target.h) / img_size.h
+    expect = box * (torch.tensor([rw, rw, rw, rw]) if rw == rh else torch.tensor([rw, rh, rw, rh]))
+    if not torch.allclose(res.bbox_xyxy.float().cpu(), expect, rtol=1e-5, atol=1e-5):
+        raise NotImplementedError("os2d_b200.decode_pyramid supports inverse box transforms that only resize "
+                                  "(got a transform that maps {} to {})".format(box.tolist(), res.bbox_xyxy.tolist()))
+    return target

@@ -112,14 +112,14 @@ int launch_pack_corr(const float* corr, int planes, int N, void* zvol, void* raw
   if (planes <= 0 || N <= 0) return kErrBadArg;
   pack_corr_kernel<<<dim3((N + 127) / 128, planes), 128, 0, st>>>(corr, N, reinterpret_cast<__half*>(zvol),
                                                                  reinterpret_cast<__half*>(rawvol));
-  OS2D_CUDA_TRY(cudaGetLastError());
+  OS2D_AFTER_LAUNCH();
   return kOk;
 }
 
 int launch_affine_grids(const float* params, int planes, int P, int N, int inverse, float* grid, cudaStream_t st) {
   if (planes <= 0 || N <= 0 || (P != 4 && P != 6)) return kErrBadArg;
   affine_grid_kernel<<<dim3((N + 127) / 128, planes), 128, 0, st>>>(params, P, N, inverse, grid);
-  OS2D_CUDA_TRY(cudaGetLastError());
+  OS2D_AFTER_LAUNCH();
   return kOk;
 }
 
@@ -127,7 +127,7 @@ int launch_resample_grid(const float* corr, const float* grid, const float* mask
                          cudaStream_t st) {
   if (planes <= 0 || C <= 0 || H < 2 || W < 2) return kErrBadArg;
   resample_grid_kernel<<<dim3((H * W + 127) / 128, planes), 128, 0, st>>>(corr, grid, mask, C, H, W, out);
-  OS2D_CUDA_TRY(cudaGetLastError());
+  OS2D_AFTER_LAUNCH();
   return kOk;
 }
 

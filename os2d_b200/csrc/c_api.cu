@@ -1,5 +1,7 @@
 // extern "C" shim of include/os2d_b200.h + host utilities (error string, tensor-map encoder).
 #include <cudaTypedefs.h>
+
+#include <atomic>
 #include <stdio.h>
 #include <string.h>
 
@@ -15,6 +17,9 @@ void set_last_error(const char* what, cudaError_t e) {
   snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 void set_last_error_msg(const char* what) { snprintf(g_err, sizeof(g_err), "%s", what); }
+
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -76,6 +81,7 @@ extern "C" {
 int os2d_b200_abi_version(void) { return 1; }
 const char* os2d_b200_last_error(void) { return os2d::g_err; }
 int os2d_b200_num_sms(void) { return num_sms_cached(); }
+unsigned long long os2d_b200_launch_count(void) { return os2d::g_launches.load(std::memory_order_relaxed); }
 
 int os2d_pack_class_features(const float* maps, int C, int D, int h, int w, int normalize, float* cf32, void* packed,
                              void* stream) {
@@ -177,6 +183,69 @@ int os2d_nms_segments(const float* boxes, const int32_t* order, const int32_t* s
   if (num_segs == 0) return kOk;
   if (!boxes || !order || !seg_offsets || !keep) return kErrBadArg;
   return launch_nms(boxes, order, seg_offsets, num_segs, iou_threshold, keep, static_cast<cudaStream_t>(stream));
+}
+
+static int fill_detect_args(DetectArgs& A, const os2d_pyramid_level* levels, int num_levels, int num_views, int n_labels,
+                            float stride_w, float stride_h, float box_w, float box_h) {
+  if (!levels || num_levels <= 0 || num_levels > kMaxPyramidLevels || num_views <= 0 || n_labels <= 0) return kErrBadArg;
+  A.L = num_levels; A.C = num_views; A.n_labels = n_labels;
+  long long sum = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    const os2d_pyramid_level& s = levels[l];
+    if (!s.loc || !s.score || s.num_anchors <= 0 || s.fm_w <= 0) return kErrBadArg;
+    A.base[l] = static_cast<long long>(num_views) * sum;
+    A.lv[l].loc = s.loc; A.lv[l].score = s.score; A.lv[l].corners = s.corners;
+    A.lv[l].N = s.num_anchors; A.lv[l].fm_w = s.fm_w;
+    A.lv[l].img_w = s.img_w; A.lv[l].img_h = s.img_h; A.lv[l].scale_x = s.scale_x; A.lv[l].scale_y = s.scale_y;
+    A.lv[l].same_scale = s.same_scale;
+    sum += s.num_anchors;
+  }
+  for (int l = num_levels; l <= kMaxPyramidLevels; ++l) A.base[l] = static_cast<long long>(num_views) * sum;
+  A.sumN = sum;
+  if (static_cast<long long>(num_views) * sum >= (1ll << 31)) {
+    set_last_error_msg("os2d_detect_pyramid: more than 2^31 (class view, anchor) pairs in one call");
+    return kErrUnsupported;
+  }
+  A.grid.stride_w = stride_w; A.grid.stride_h = stride_h; A.grid.box_w = box_w; A.grid.box_h = box_h;
+  return kOk;
+}
+
+int os2d_detect_pyramid(const os2d_pyramid_level* levels, int num_levels, int num_views, const int32_t* view_offsets,
+                        const int32_t* view_ids, int n_labels, int max_views_per_label, float stride_w, float stride_h,
+                        float box_w, float box_h, float score_thr, double iou_threshold, int32_t* cand_ws, uint64_t* key_ws, int32_t* out_ids,
+                        int32_t* counts, int32_t* offsets, uint32_t* done_counter, void* stream) {
+  if (!view_offsets || !view_ids || !cand_ws || !out_ids || !counts || !offsets || !done_counter || max_views_per_label <= 0)
+    return kErrBadArg;
+  DetectArgs A;
+  const int rc = fill_detect_args(A, levels, num_levels, num_views, n_labels, stride_w, stride_h, box_w, box_h);
+  if (rc != kOk) return rc;
+  if (!key_ws && static_cast<long long>(max_views_per_label) * A.sumN > 10000) {
+    set_last_error_msg("os2d_detect_pyramid: key_ws is required when a label can hold more than one NMS chunk of candidates");
+    return kErrBadArg;
+  }
+  A.score_thr = score_thr; A.iou_thr = iou_threshold;
+  A.view_off = view_offsets; A.view_ids = view_ids;
+  A.cand = cand_ws; A.keys = reinterpret_cast<unsigned long long*>(key_ws); A.out_ids = out_ids;
+  A.counts = counts; A.offsets = offsets; A.done = done_counter;
+  return launch_label_nms(A, static_cast<cudaStream_t>(stream));
+}
+
+int os2d_gather_detections(const os2d_pyramid_level* levels, int num_levels, int num_views, const int32_t* view_offsets,
+                           int n_labels, float stride_w, float stride_h, float box_w, float box_h, const int32_t* out_ids,
+                           const int32_t* counts, const int32_t* offsets, const int64_t* label_values, float* boxes,
+                           float* scores, int64_t* labels, float* anchors, float* corners, void* stream) {
+  if (!view_offsets || !out_ids || !counts || !offsets || !label_values || !boxes || !scores || !labels || !anchors)
+    return kErrBadArg;
+  DetectArgs A;
+  const int rc = fill_detect_args(A, levels, num_levels, num_views, n_labels, stride_w, stride_h, box_w, box_h);
+  if (rc != kOk) return rc;
+  if (corners) for (int l = 0; l < num_levels; ++l) if (!levels[l].corners) return kErrBadArg;
+  A.score_thr = 0.f; A.iou_thr = 0.0;
+  A.view_off = view_offsets; A.view_ids = nullptr;
+  A.cand = nullptr; A.keys = nullptr; A.out_ids = const_cast<int32_t*>(out_ids);
+  A.counts = const_cast<int32_t*>(counts); A.offsets = const_cast<int32_t*>(offsets); A.done = nullptr;
+  return launch_gather_detections(A, reinterpret_cast<const long long*>(label_values), boxes, scores,
+                                  reinterpret_cast<long long*>(labels), anchors, corners, static_cast<cudaStream_t>(stream));
 }
 
 int os2d_voc_match(const float* det_boxes, const int* det_img, const int* det_label, const float* gt_boxes,

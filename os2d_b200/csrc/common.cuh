@@ -22,6 +22,28 @@ enum : int { kOk = 0, kErrBadArg = -1, kErrCuda = -2, kErrUnsupported = -3, kErr
 
 void set_last_error(const char* what, cudaError_t e);
 void set_last_error_msg(const char* what);
+// kernel-launch counter of the library (os2d_b200_launch_count): every launcher reports its launches
+void note_launch();
+#define OS2D_AFTER_LAUNCH()                    \
+  do {                                         \
+    OS2D_CUDA_TRY(cudaGetLastError());         \
+    os2d::note_launch();                       \
+  } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: set it once per (kernel, device), keyed
+// on the current device like num_sms_cached() in c_api.cu (a per-process flag breaks the first launch on a second GPU).
+constexpr int kMaxDevices = 64;
+#define OS2D_SET_MAX_DYN_SMEM(kernel, bytes)                                                                   \
+  do {                                                                                                         \
+    static bool _done[os2d::kMaxDevices] = {};                                                                 \
+    int _dev = 0;                                                                                              \
+    OS2D_CUDA_TRY(cudaGetDevice(&_dev));                                                                       \
+    if (_dev < 0 || _dev >= os2d::kMaxDevices) { os2d::set_last_error_msg("device index out of range"); return os2d::kErrUnsupported; } \
+    if (!_done[_dev]) {                                                                                        \
+      OS2D_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes))); \
+      _done[_dev] = true;                                                                                      \
+    }                                                                                                          \
+  } while (0)
 
 // ----------------------------------------------------------------------------------------------
 // small PTX wrappers

@@ -399,14 +399,10 @@ static int launch_t(const ConvLayerDesc& L, const void* in_vol, const void* wblo
   P.alpha = alpha;
   P.beta = beta;
   P.out = out;
-  static bool attr_set = false;
-  if (!attr_set) {
-    OS2D_CUDA_TRY(cudaFuncSetAttribute(conv_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-    attr_set = true;
-  }
+  OS2D_SET_MAX_DYN_SMEM(conv_kernel<KS>, G::SMEM_BYTES);
   const int grid = P.total_tiles < num_sms ? P.total_tiles : num_sms;
   conv_kernel<KS><<<grid, THREADS, G::SMEM_BYTES, st>>>(map_in, P);
-  OS2D_CUDA_TRY(cudaGetLastError());
+  OS2D_AFTER_LAUNCH();
   return kOk;
 }
 

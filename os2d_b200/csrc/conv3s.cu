@@ -207,14 +207,10 @@ int launch_conv3s(const void* h2_vol, const void* wblob, const float* bias, cons
   Pm.inv_scale = inv_scale;
   Pm.bias = bias;
   Pm.out = out;
-  static bool attr_set = false;
-  if (!attr_set) {
-    OS2D_CUDA_TRY(cudaFuncSetAttribute(conv3s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  OS2D_SET_MAX_DYN_SMEM(conv3s_kernel, SMEM_BYTES);
   const int grid = Pm.total_tiles < num_sms ? Pm.total_tiles : num_sms;
   conv3s_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(map_in, Pm);
-  OS2D_CUDA_TRY(cudaGetLastError());
+  OS2D_AFTER_LAUNCH();
   return kOk;
 }
 

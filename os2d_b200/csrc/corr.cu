@@ -342,11 +342,7 @@ static int launch_t(const void* img_packed, const void* cls_packed, int B, int C
   P.total_tiles = B * C * (kTwoCta ? (P.MT + 1) / 2 : P.MT);
   P.zvol = reinterpret_cast<__half*>(zvol);
   P.rawvol = reinterpret_cast<__half*>(rawvol);
-  static bool attr_set = false;
-  if (!attr_set) {
-    OS2D_CUDA_TRY(cudaFuncSetAttribute(corr_kernel<kTwoCta>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
-    attr_set = true;
-  }
+  OS2D_SET_MAX_DYN_SMEM(corr_kernel<kTwoCta>, K::SMEM_BYTES);
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   if (kTwoCta) {
@@ -364,6 +360,7 @@ static int launch_t(const void* img_packed, const void* cls_packed, int B, int C
   cfg.dynamicSmemBytes = K::SMEM_BYTES;
   cfg.stream = st;
   OS2D_CUDA_TRY(cudaLaunchKernelEx(&cfg, corr_kernel<kTwoCta>, map_img, map_cls, P));
+  os2d::note_launch();
   return kOk;
 }
 

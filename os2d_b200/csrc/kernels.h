@@ -75,6 +75,37 @@ int launch_decode(const DecodeArgs& A, const float* loc, const float* score, con
 int launch_nms(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int num_segs, double iou_thr,
                uint8_t* keep, cudaStream_t st);
 
+// fused decode + per-label NMS over a pyramid (detect.cu)
+constexpr int kMaxPyramidLevels = 12;
+struct DetectLevel {
+  const float* loc;       // [C,4,N]
+  const float* score;     // [C,N]
+  const float* corners;   // [C,8,N] or nullptr
+  int N, fm_w;
+  float img_w, img_h, scale_x, scale_y;
+  int same_scale;
+};
+struct DetectArgs {
+  int L, C, n_labels;
+  long long sumN;                          // anchors of all levels
+  long long base[kMaxPyramidLevels + 1];   // flat index base of level l = C * sum_{k<l} N_k
+  DetectLevel lv[kMaxPyramidLevels];
+  struct { float stride_w, stride_h, box_w, box_h; } grid;
+  float score_thr;
+  double iou_thr;
+  const int* view_off;     // device [n_labels + 1]: class views of label i = view_ids[view_off[i] .. view_off[i+1])
+  const int* view_ids;     // device [C]
+  int* cand;               // workspace [C * sumN]
+  unsigned long long* keys;   // workspace [C * sumN] (only touched when a label needs more than one NMS chunk)
+  int* out_ids;            // [C * sumN]: survivors of label i at view_off[i] * sumN, score-descending
+  int* counts;             // [n_labels]
+  int* offsets;            // [n_labels + 1] exclusive scan of counts (written by the last CTA)
+  unsigned int* done;      // zero-initialised counter, reset by the kernel
+};
+int launch_label_nms(const DetectArgs& A, cudaStream_t st);
+int launch_gather_detections(const DetectArgs& A, const long long* label_values, float* boxes, float* scores, long long* labels,
+                             float* anchors, float* corners, cudaStream_t st);
+
 // image pyramid level (pyramid.cu): Pillow-exact bilinear resize + ToTensor + Normalize
 int launch_resize_level(const uint8_t* img, int H, int W, int out_h, int out_w, const int* xbounds, const int* xcoeffs, int xk,
                         const int* ybounds, const int* ycoeffs, int yk, const float* mean, const float* stdv, uint8_t* tmp,

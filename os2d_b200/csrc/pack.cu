@@ -204,6 +204,7 @@ static int launch_pack_class_any(const float* maps, const float* const* map_ptrs
   cfg.attrs = attr; cfg.numAttrs = 1;
   OS2D_CUDA_TRY(cudaLaunchKernelEx(&cfg, pack_class_kernel, maps, map_ptrs, hw, h, w, D, normalize, cf32,
                                    reinterpret_cast<__half*>(packed)));
+  os2d::note_launch();
   return kOk;
 }
 
@@ -222,7 +223,7 @@ int launch_pack_class_ragged(const float* const* map_ptrs, const int* hw, int C,
 int launch_pack_image(const float* fm, int B, int D, int N, float* inv_ws, void* packed, cudaStream_t st) {
   if (B <= 0 || D <= 0 || N <= 0 || (D % 64) != 0) return kErrBadArg;
   image_pack_kernel<<<dim3((N + 31) / 32, B), 256, 0, st>>>(fm, D, N, inv_ws, reinterpret_cast<__half*>(packed));
-  OS2D_CUDA_TRY(cudaGetLastError());
+  OS2D_AFTER_LAUNCH();
   return kOk;
 }
 

@@ -7,6 +7,7 @@
 // All float arithmetic uses explicit round-to-nearest intrinsics so that no FMA contraction changes a decision
 // relative to the scalar CPU order of operations.
 #include "common.cuh"
+#include "decode.cuh"
 #include "kernels.h"
 
 namespace os2d {
@@ -18,31 +19,15 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs A, const float* 
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
   if (n >= A.N) return;
-  const int y = n / A.fm_w, x = n - y * A.fm_w;
-  // anchor (box_coder.py:42-59): centre (i + 0.5) * stride, xyxy = c -/+ size / 2
-  const float cx = __fmul_rn(static_cast<float>(x) + 0.5f, A.stride_w), cy = __fmul_rn(static_cast<float>(y) + 0.5f, A.stride_h);
-  const float hw = A.box_w / 2.0f, hh = A.box_h / 2.0f;
-  const float ax1 = __fsub_rn(cx, hw), ay1 = __fsub_rn(cy, hh), ax2 = __fadd_rn(cx, hw), ay2 = __fadd_rn(cy, hh);
-  const float aw = __fsub_rn(ax2, ax1), ah = __fsub_rn(ay2, ay1);
-  const float actr_x = __fadd_rn(ax1, __fmul_rn(0.5f, aw)), actr_y = __fadd_rn(ay1, __fmul_rn(0.5f, ah));
-
+  const DecodeArgs& G = A;
   const float* l = loc + static_cast<size_t>(c) * 4 * A.N + n;
-  const float dx = __fdiv_rn(l[0], 10.0f), dy = __fdiv_rn(l[A.N], 10.0f);
-  const float kClip = 4.135166556742356f;   // log(1000 / 16)
-  const float dw = fminf(__fdiv_rn(l[2 * static_cast<size_t>(A.N)], 5.0f), kClip);
-  const float dh = fminf(__fdiv_rn(l[3 * static_cast<size_t>(A.N)], 5.0f), kClip);
-  const float pcx = __fadd_rn(__fmul_rn(dx, aw), actr_x), pcy = __fadd_rn(__fmul_rn(dy, ah), actr_y);
-  const float pw = __fmul_rn(expf(dw), aw), ph = __fmul_rn(expf(dh), ah);
-  const float cw = __fmul_rn(0.5f, pw), chh = __fmul_rn(0.5f, ph);
-  float x1 = __fsub_rn(pcx, cw), y1 = __fsub_rn(pcy, chh), x2 = __fadd_rn(pcx, cw), y2 = __fadd_rn(pcy, chh);
-  x1 = fminf(fmaxf(x1, 0.f), A.img_w); x2 = fminf(fmaxf(x2, 0.f), A.img_w);
-  y1 = fminf(fmaxf(y1, 0.f), A.img_h); y2 = fminf(fmaxf(y2, 0.f), A.img_h);
-  const bool empty = (y2 <= y1) || (x2 <= x1);
-  const float s = score[static_cast<size_t>(c) * A.N + n];
-  valid[static_cast<size_t>(c) * A.N + n] = (s > A.score_thr) && !empty;
   const float sx = A.scale_x, sy = A.same_scale ? A.scale_x : A.scale_y;
-  boxes[static_cast<size_t>(c) * A.N + n] = make_float4(__fmul_rn(x1, sx), __fmul_rn(y1, sy), __fmul_rn(x2, sx), __fmul_rn(y2, sy));
-  if (c == 0) anchors_out[n] = make_float4(__fmul_rn(ax1, sx), __fmul_rn(ay1, sy), __fmul_rn(ax2, sx), __fmul_rn(ay2, sy));
+  const Decoded d = decode_one(G, n, A.fm_w, l[0], l[A.N], l[2 * static_cast<size_t>(A.N)], l[3 * static_cast<size_t>(A.N)],
+                               A.img_w, A.img_h, sx, sy);
+  const float s = score[static_cast<size_t>(c) * A.N + n];
+  valid[static_cast<size_t>(c) * A.N + n] = (s > A.score_thr) && !d.empty;
+  boxes[static_cast<size_t>(c) * A.N + n] = d.box;
+  if (c == 0) anchors_out[n] = d.anchor;
   if (corners != nullptr) {
     const float* co = corners + static_cast<size_t>(c) * 8 * A.N + n;
     float* dst = corners_out + (static_cast<size_t>(c) * A.N + n) * 8;
@@ -56,7 +41,7 @@ int launch_decode(const DecodeArgs& A, const float* loc, const float* score, con
   if (A.C <= 0 || A.N <= 0 || A.fm_w <= 0) return kErrBadArg;
   decode_kernel<<<dim3((A.N + 255) / 256, A.C), 256, 0, st>>>(A, loc, score, corners, reinterpret_cast<float4*>(boxes),
                                                             reinterpret_cast<float4*>(anchors_out), corners_out, valid);
-  OS2D_CUDA_TRY(cudaGetLastError());
+  OS2D_AFTER_LAUNCH();
   return kOk;
 }
 
@@ -98,13 +83,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const float4* __res
     const float iarea = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
     for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
       if (supp[j]) continue;
-      const float4 bj = sb[j];
-      const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y), xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
-      const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
-      const float inter = __fmul_rn(w, h);
-      const float jarea = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
-      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, jarea), inter));
-      if (static_cast<double>(ovr) > thr) supp[j] = 1;
+      if (iou_exceeds(bi, iarea, sb[j], thr)) supp[j] = 1;
     }
     __syncthreads();
   }
@@ -115,13 +94,9 @@ int launch_nms(const float* boxes, const int32_t* order, const int32_t* seg_offs
                uint8_t* keep, cudaStream_t st) {
   if (num_segs <= 0) return kOk;
   const size_t smem = static_cast<size_t>(kNmsMaxSeg) * (sizeof(float4) + 1);
-  static bool attr_set = false;
-  if (!attr_set) {
-    OS2D_CUDA_TRY(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_set = true;
-  }
+  OS2D_SET_MAX_DYN_SMEM(nms_kernel, smem);
   nms_kernel<<<num_segs, kNmsThreads, smem, st>>>(reinterpret_cast<const float4*>(boxes), order, seg_offsets, iou_thr, keep);
-  OS2D_CUDA_TRY(cudaGetLastError());
+  OS2D_AFTER_LAUNCH();
   return kOk;
 }
 

@@ -67,11 +67,11 @@ int launch_resize_level(const uint8_t* img, int H, int W, int out_h, int out_w, 
                         float* out, uint8_t* out_u8, cudaStream_t st) {
   if (H <= 0 || W <= 0 || out_h <= 0 || out_w <= 0 || xk <= 0 || yk <= 0 || H > 65535 || out_h > 65535) return kErrBadArg;
   resize_h_kernel<<<dim3((out_w + 255) / 256, H), 256, 0, st>>>(img, H, W, out_w, xbounds, xcoeffs, xk, tmp);
-  OS2D_CUDA_TRY(cudaGetLastError());
+  OS2D_AFTER_LAUNCH();
   resize_v_norm_kernel<<<dim3((out_w + 255) / 256, out_h), 256, 0, st>>>(tmp, H, out_w, out_h, ybounds, ycoeffs, yk, mean[0],
                                                                         mean[1], mean[2], stdv[0], stdv[1], stdv[2], out,
                                                                         out_u8);
-  OS2D_CUDA_TRY(cudaGetLastError());
+  OS2D_AFTER_LAUNCH();
   return kOk;
 }
 

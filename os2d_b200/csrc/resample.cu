@@ -6,22 +6,57 @@
 //   resample + masked mean       os2d/modeling/head.py:439-520 (inner 11x11 points, channel k = j*15 + i)
 //   box / corners / loc          os2d/modeling/head.py:404-433, box_coder.py:306-317, bounding_box.py:267-277
 // Lanes run along x so that the 4 taps of a grid point are near-coalesced reads of one channel plane.
+//
+// The kernel is a template on its output sink: LocalSink writes the 13 output planes of a location into local tensors (or
+// this rank's slice of a gather buffer); PeerSink is K3 fused with its collective (multi-GPU, class-axis sharding): every
+// thread stores its 13 outputs into this rank's slice of the [G,B,C/G,13,N] gather buffer of EVERY rank through
+// peer-mapped pointers (symmetric memory over NVLink 5 / NVSwitch), 13 coalesced 128 B row stores per warp and peer, and a
+// device-side barrier across the ranks (os2d_b200/dist.py) replaces the all-gather.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace os2d {
+
+struct LocalSink {
+  float* score; float* loc; float* corners;
+  long long score_ps, loc_ps, corners_ps;          // plane strides (floats)
+  __device__ __forceinline__ void store(int plane, int N, int pix, float sc, const float (&l)[4], const float (&X)[4],
+                                        const float (&Y)[4]) const {
+    score[static_cast<size_t>(plane) * score_ps + pix] = sc;
+    float* lo = loc + static_cast<size_t>(plane) * loc_ps + pix;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) lo[static_cast<size_t>(q) * N] = l[q];
+    float* co = corners + static_cast<size_t>(plane) * corners_ps + pix;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      co[static_cast<size_t>(2 * q) * N] = X[q];
+      co[static_cast<size_t>(2 * q + 1) * N] = Y[q];
+    }
+  }
+};
+
+struct PeerSink {
+  float* const* peers; int n_peers;                 // base of every rank's gather buffer (peer-mapped)
+  long long score_off, loc_off, corners_off, plane_stride;
+  __device__ __forceinline__ void store(int plane, int N, int pix, float sc, const float (&l)[4], const float (&X)[4],
+                                        const float (&Y)[4]) const {
+    const size_t po = static_cast<size_t>(plane) * plane_stride + pix;
+    for (int p = 0; p < n_peers; ++p) {
+      const LocalSink s{peers[p] + score_off + po, peers[p] + loc_off + po, peers[p] + corners_off + po, 0, 0, 0};
+      s.store(0, N, 0, sc, l, X, Y);
+    }
+  }
+};
 
 __device__ __forceinline__ float lin15(int i) {
   const float step = 2.0f / 14.0f;
   return (i < 7) ? (-1.0f + step * i) : (1.0f - step * (14 - i));
 }
 
+template <typename Sink>
 __global__ void __launch_bounds__(128, 12) resample_kernel(const __half* __restrict__ raw, const float* __restrict__ params,
                                                         int P, int H, int W, int inverse, float stride_w,
-                                                        float stride_h, float box_w, float box_h,
-                                                        float* __restrict__ score, float* __restrict__ loc,
-                                                        float* __restrict__ corners, long long score_ps,
-                                                        long long loc_ps, long long corners_ps) {
+                                                        float stride_h, float box_w, float box_h, const Sink sink) {
   const int N = H * W;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   const int plane = blockIdx.y;
@@ -81,7 +116,7 @@ __global__ void __launch_bounds__(128, 12) resample_kernel(const __half* __restr
       acc += fmaf(wys[i], bot - top, top);
     }
   }
-  score[static_cast<size_t>(plane) * score_ps + pix] = acc * (1.0f / 121.0f);
+  const float sc = acc * (1.0f / 121.0f);
 
   // ---- box = bbox of the transformed grid (extremes are at the 4 corner points), corners, loc ----
   // anchor: centre (x + 0.5) * stride, size box (240 = 16 * 14 + 16 for the ResNet C4 backbones, head.py:216-238)
@@ -96,23 +131,15 @@ __global__ void __launch_bounds__(128, 12) resample_kernel(const __half* __restr
     X[q] = fmaf(gx, hbw, acx);
     Y[q] = fmaf(gy, hbh, acy);
   }
-  float* co = corners + static_cast<size_t>(plane) * corners_ps + pix;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    co[static_cast<size_t>(2 * q) * N] = X[q];
-    co[static_cast<size_t>(2 * q + 1) * N] = Y[q];
-  }
   const float x1 = fminf(fminf(X[0], X[1]), fminf(X[2], X[3])), y1 = fminf(fminf(Y[0], Y[1]), fminf(Y[2], Y[3]));
   float x2 = fmaxf(fmaxf(X[0], X[1]), fmaxf(X[2], X[3])), y2 = fmaxf(fmaxf(Y[0], Y[1]), fmaxf(Y[2], Y[3]));
   if (x1 + 1.0f > x2) x2 = x1 + 1.0f;
   if (y1 + 1.0f > y2) y2 = y1 + 1.0f;
   const float gw = x2 - x1, gh = y2 - y1;
   const float gcx = x1 + 0.5f * gw, gcy = y1 + 0.5f * gh;
-  float* lo = loc + static_cast<size_t>(plane) * loc_ps + pix;
-  lo[0] = 10.0f * (gcx - acx) / box_w;
-  lo[N] = 10.0f * (gcy - acy) / box_h;
-  lo[2 * static_cast<size_t>(N)] = 5.0f * logf(gw / box_w);
-  lo[3 * static_cast<size_t>(N)] = 5.0f * logf(gh / box_h);
+  const float l[4] = {10.0f * (gcx - acx) / box_w, 10.0f * (gcy - acy) / box_h, 5.0f * logf(gw / box_w),
+                      5.0f * logf(gh / box_h)};
+  sink.store(plane, N, pix, sc, l, X, Y);
 }
 
 int launch_resample(const void* rawvol, const float* params, int planes, int P, int H, int W, int inverse,
@@ -120,10 +147,24 @@ int launch_resample(const void* rawvol, const float* params, int planes, int P, 
                     float* corners, long long score_ps, long long loc_ps, long long corners_ps, cudaStream_t st) {
   if (planes <= 0 || (P != 4 && P != 6) || H < 2 || W < 2) return kErrBadArg;
   const int N = H * W;
-  resample_kernel<<<dim3((N + 127) / 128, planes), 128, 0, st>>>(reinterpret_cast<const __half*>(rawvol), params, P, H,
-                                                              W, inverse, stride_w, stride_h, box_w, box_h, score, loc,
-                                                              corners, score_ps, loc_ps, corners_ps);
-  OS2D_CUDA_TRY(cudaGetLastError());
+  const LocalSink sink{score, loc, corners, score_ps, loc_ps, corners_ps};
+  resample_kernel<LocalSink><<<dim3((N + 127) / 128, planes), 128, 0, st>>>(reinterpret_cast<const __half*>(rawvol), params,
+                                                                         P, H, W, inverse, stride_w, stride_h, box_w,
+                                                                         box_h, sink);
+  OS2D_AFTER_LAUNCH();
+  return kOk;
+}
+
+int launch_resample_p2p(const void* rawvol, const float* params, int planes, int P, int H, int W, int inverse,
+                        float stride_w, float stride_h, float box_w, float box_h, float* const* peers, int n_peers,
+                        long long score_off, long long loc_off, long long corners_off, long long plane_stride, cudaStream_t st) {
+  if (planes <= 0 || (P != 4 && P != 6) || H < 2 || W < 2 || n_peers <= 0 || !peers) return kErrBadArg;
+  const int N = H * W;
+  const PeerSink sink{peers, n_peers, score_off, loc_off, corners_off, plane_stride};
+  resample_kernel<PeerSink><<<dim3((N + 127) / 128, planes), 128, 0, st>>>(reinterpret_cast<const __half*>(rawvol), params,
+                                                                        P, H, W, inverse, stride_w, stride_h, box_w,
+                                                                        box_h, sink);
+  OS2D_AFTER_LAUNCH();
   return kOk;
 }
 

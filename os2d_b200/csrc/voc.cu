@@ -43,7 +43,7 @@ int launch_voc_match(const float* det_boxes, const int* det_img, const int* det_
   voc_match_kernel<<<(n_det + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(det_boxes), det_img, det_label,
                                                        reinterpret_cast<const float4*>(gt_boxes), gt_label, gt_offsets, n_det,
                                                        iou_thr, gt_index);
-  OS2D_CUDA_TRY(cudaGetLastError());
+  OS2D_AFTER_LAUNCH();
   return kOk;
 }
 

@@ -110,6 +110,7 @@ class TransformationNet(nn.Module):
         self._packed_key = key
         return self._packed
 
+    @_cabi.on_device_of
     def forward(self, corr_maps):
         """corr_maps [NB,225,H,W] fp32 -> transform parameters [NB,P,H,W] (head.py:648-655).  Stand-alone entry point
         (Os2dHead.forward never builds the fp32 correlation volume): the maps are normalised / packed by
@@ -137,6 +138,7 @@ def _require_inference(t, module):
         raise RuntimeError("os2d_b200 requires CUDA tensors (no CPU path)")
 
 
+@_cabi.on_device_of
 def run_transform_convs(pw, P, zvol, planes, H, W, timed=None):
     """z volume [planes,30,N,8] -> parameters [planes,P,N] through the three conv kernels (os2d_transform_conv 1..3)."""
     lib = _cabi.load()
@@ -285,6 +287,7 @@ class Os2dAlignment(nn.Module):
             a, b, c, d, tx, ty = ia, ib, ic, id_, itx, ity
         return torch.stack([a, b, tx, c, d, ty], dim=1).view(-1, 2, 3)
 
+    @_cabi.on_device_of
     def forward(self, corr_maps):
         """corr_maps [NB,225,H,W] -> grids of transformed points [NB,H,W,15,15,2] in the local coordinate system of every
         location (head.py:155-193).  Stand-alone entry point: the fused path never materialises this tensor."""
@@ -332,6 +335,7 @@ class Os2dHeadCreator(nn.Module):
                         self.box_grid_generator_feature_map_level, _from_raw_maps=True)
 
 
+@_cabi.on_device_of
 def _prepare_class_operands(feature_maps, normalized=True):
     """list of [1,D,h,w] CUDA fp32 maps -> (cf32 [C,D,15,15], packed fp16 [C,240,D]): ONE kernel launch for the whole
     (possibly ragged) set, os2d_pack_class_features_ragged; os2d_pack_class_features when the list is a sliced batch."""
@@ -401,6 +405,8 @@ class Os2dHead(nn.Module):
         self.class_pool_mask = mask / mask.sum(dim=(2, 3), keepdim=True)     # head.py:295-302
         self.aligner = aligner
         self.max_planes_per_call = 4096
+        self.workspace_bytes = None      # byte bound of the per-call workspace; None = half of the free device memory
+        self._cmax_cache = {}
         self.supports_out_views = True
         # optional per-stage CUDA-event timing (bench.py): list of (stage, start_event, end_event) when not None
         self.profile_events = None
@@ -419,9 +425,26 @@ class Os2dHead(nn.Module):
         sub.class_pool_mask = self.class_pool_mask.index_select(0, idx)
         sub.aligner = self.aligner
         sub.max_planes_per_call = self.max_planes_per_call
+        sub.workspace_bytes = self.workspace_bytes
+        sub._cmax_cache = {}
         sub.supports_out_views = True
         sub.profile_events = None
         return sub
+
+    def _classes_per_chunk(self, B, N, P, dev):
+        """Classes per workspace chunk: bounded in planes (max_planes_per_call) AND in bytes - one (image, class) plane of
+        the z / raw / h1 / h2 / params volumes takes ~1.47 KB per location, so 1000+ class views on a 128x128..150x150
+        pyramid level would otherwise ask for > 100 GB in one chunk (the reference's per-class loop never does)."""
+        key = (B, N, P, self.max_planes_per_call, self.workspace_bytes)
+        if key not in self._cmax_cache:
+            per_plane = N * (Z_CHUNKS * 16 + CORR_CH * 2 + 256 + 256 + 4 * P)
+            budget = self.workspace_bytes
+            if budget is None:
+                free, _ = torch.cuda.mem_get_info(dev)
+                cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+                budget = (free + cached) // 2
+            self._cmax_cache[key] = max(1, min(self.max_planes_per_call, int(budget) // per_plane) // B)
+        return self._cmax_cache[key]
 
     def _timed(self, name, fn, *a):
         if self.profile_events is None:
@@ -433,14 +456,17 @@ class Os2dHead(nn.Module):
         self.profile_events.append((name, e0, e1))
         return rc
 
-    def forward(self, feature_maps, out_views=None, out_peers=None):
+    @_cabi.on_device_of
+    def forward(self, feature_maps, out_views=None, out_peers=None, _before_resample=None):
         """feature_maps [B,D,H,W] -> (loc [B,C,4,H,W], rec [B,C,1,H,W], rec_transform_detached (same tensor under
         no-grad, head.py:400-402), corners [B,C,8,H,W]).  ``out_views`` (extension, default None): (score, loc, corners)
         strided views [B,C,k,H*W] to write into instead of fresh tensors; the call then returns None.
         ``out_peers`` (extension, multi-GPU): ``(ptrs, slice_offset, per)`` - int64 CUDA tensor of the base pointers of every
         rank's [G,B,per,13,N] gather buffer (peer-mapped), the float offset of THIS rank's slice in such a buffer and the
         number of class slots per rank; K3 then stores its outputs into all those buffers itself (csrc/resample_p2p.cu)
-        and the call returns None - the caller synchronises the ranks before reading."""
+        and the call returns None - the caller synchronises the ranks before reading; ``_before_resample`` (callable) is
+        invoked once on the launch stream right before the first K3 launch (os2d_b200.dist enqueues the cross-rank
+        "slot is free" barrier there, so K1 and the convolutions never wait for the other ranks)."""
         if torch.is_grad_enabled() and (feature_maps.requires_grad or
                                         any(p.requires_grad for p in self.aligner.parameters())):
             raise RuntimeError("os2d_b200.Os2dHead implements inference only; call it under torch.no_grad() "
@@ -484,7 +510,7 @@ class Os2dHead(nn.Module):
             loc = score = corners = None
 
         # class chunks bound the workspace (z / raw / hidden volumes); classes are independent in eval mode
-        cmax = max(1, self.max_planes_per_call // B)
+        cmax = self._classes_per_chunk(B, N, P, dev)
         for c0 in range(0, C, cmax):
             cc = min(cmax, C - c0)
             planes = B * cc
@@ -494,6 +520,9 @@ class Os2dHead(nn.Module):
             _cabi.check(self._timed("corr", lib.os2d_correlate, _cabi.ptr(img_packed), _cabi.ptr(cls), B, cc, D, H, W,
                                     _cabi.ptr(zvol), _cabi.ptr(rawvol), st), "os2d_correlate")
             params = run_transform_convs(pw, P, zvol, planes, H, W, timed=self._timed)
+            if _before_resample is not None:
+                _before_resample()
+                _before_resample = None
             if out_peers is not None:
                 # K3 + collective in one kernel: outputs go to this rank's slice of every rank's gather buffer
                 ptrs, slice_off, per = out_peers
@@ -523,6 +552,7 @@ class Os2dHead(nn.Module):
         return loc, score, score, corners
 
     @staticmethod
+    @_cabi.on_device_of
     def resample_of_correlation_map_fast(corr_maps, resampling_grids_grid_coord, class_pool_mask):
         """corr_maps [B,C,225,H,W], grids [B,C,H,W,15,15,2] (unit coordinates of the feature map), mask [C,1,15,15] ->
         pooled matches [B,C,1,H,W] (head.py:439-520; `_simple` :523-594 computes the same quantity).  Stand-alone entry

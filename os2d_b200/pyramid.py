@@ -58,6 +58,7 @@ def _as_u8_hwc(image, device):
     return t.to(device).contiguous()
 
 
+@_cabi.on_device_of
 def resize_normalize(img_u8, out_w, out_h, mean, std, return_bytes=False):
     """One pyramid level: CUDA uint8 [H,W,3] -> fp32 [3,out_h,out_w] (and optionally the resized bytes [out_h,out_w,3])."""
     if img_u8.device.type != "cuda":

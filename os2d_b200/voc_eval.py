@@ -107,6 +107,7 @@ def _average_precision(lab, counts, seg_start, prec, rec, valid, L, use_07_metri
     return ap
 
 
+@_cabi.on_device_of
 def do_voc_evaluation(predictions, gt_boxes, iou_thresh=0.5, use_07_metric=False):
     """predictions / gt_boxes: lists of BoxList (one per image; fields "labels", "scores" / "labels", optional
     "difficult").  Returns the dict of the reference: ap_per_class, map, map_weighted, recall_per_class, recall, n_pos,

@@ -122,3 +122,59 @@ def test_decode_pyramid_matches_oracle_random(across):
     np.testing.assert_allclose(res.bbox_xyxy.cpu().numpy(), ref["boxes"], rtol=1e-5, atol=1e-2)
     np.testing.assert_allclose(res.get_field("transform_corners").cpu().numpy(), ref["transform_corners"], rtol=1e-6, atol=1e-3)
     assert 11 not in res.get_field("labels").tolist()
+
+
+def _same_detections(a, b):
+    assert len(a) == len(b)
+    assert torch.equal(a.get_field("labels"), b.get_field("labels"))
+    assert torch.equal(a.get_field("scores"), b.get_field("scores"))
+    assert torch.equal(a.bbox_xyxy, b.bbox_xyxy)
+    assert torch.equal(a.get_field("default_boxes").bbox_xyxy, b.get_field("default_boxes").bbox_xyxy)
+    if a.has_field("transform_corners"):
+        assert torch.equal(a.get_field("transform_corners"), b.get_field("transform_corners"))
+
+
+@pytest.mark.parametrize("case", ["cfg2_all_anchors", "seven_levels_chunked", "merged_views_chunked", "quantised_ties"])
+def test_fused_decode_nms_equals_staged_path(case):
+    """The two-launch fused path (csrc/detect.cu) against the staged round-1 path (decode kernel + torch ordering + segment
+    NMS kernel, itself pinned by the goldens above) at sizes the CPU oracle cannot reach: every field bit for bit."""
+    from os2d_b200.structures import FeatureMapSize
+    from os2d_b200.box_coder import make_resize_transform
+    g = torch.Generator().manual_seed(321)
+    if case == "cfg2_all_anchors":           # BASELINE configs[1]: 100 classes x 6400 anchors, every anchor a candidate
+        sides, C, thr, ids, quant = [80], 100, float("-inf"), list(range(100)), 0
+    elif case == "seven_levels_chunked":     # configs[3] pyramid: 52 740 anchors per class, > 10000 candidates per label
+        sides, C, thr, ids, quant = [40, 50, 64, 80, 96, 112, 128], 6, 0.55, [5, 1, 9, 2, 7, 3], 0
+    elif case == "merged_views_chunked":     # duplicated class ids: views merge into one label before NMS
+        sides, C, thr, ids, quant = [64, 80], 6, 0.3, [4, 4, 8, 4, 8, 2], 0
+    else:                                    # tied scores: stable order by candidate position
+        sides, C, thr, ids, quant = [50, 64], 4, 0.4, [0, 1, 2, 3], 32
+    loc_pyr = [(torch.randn(C, 4, s * s, generator=g) * 1.2).cuda() for s in sides]
+    cls_pyr = [torch.rand(C, s * s, generator=g) for s in sides]
+    if quant:
+        cls_pyr = [(t * quant).round() / quant for t in cls_pyr]
+    cls_pyr = [t.cuda() for t in cls_pyr]
+    cor_pyr = [(torch.randn(C, 8, s * s, generator=g) * 100).cuda() for s in sides]
+    sizes = [FeatureMapSize(w=16 * s, h=16 * s) for s in sides]
+    inv = [make_resize_transform(FeatureMapSize(w=1280, h=1280)) for _ in sides]
+    coder = _coder()
+    kw = dict(nms_score_threshold=thr, nms_iou_threshold=0.3, inverse_box_transforms=inv, transform_corners_pyramid=cor_pyr)
+    fused = coder.decode_pyramid(loc_pyr, cls_pyr, sizes, ids, **kw)
+    staged = coder.decode_pyramid_staged(loc_pyr, cls_pyr, sizes, ids, **kw)
+    assert len(fused) > 0
+    _same_detections(fused, staged)
+    again = coder.decode_pyramid(loc_pyr, cls_pyr, sizes, ids, **kw)     # workspace / counter reuse
+    _same_detections(fused, again)
+
+
+def test_fused_decode_nms_no_candidates_and_no_corners():
+    from os2d_b200.structures import FeatureMapSize
+    g = torch.Generator().manual_seed(4)
+    loc = [torch.randn(3, 4, 400, generator=g).cuda()]
+    cls = [torch.rand(3, 400, generator=g).cuda()]
+    sizes = [FeatureMapSize(w=320, h=320)]
+    none = _coder().decode_pyramid(loc, cls, sizes, [0, 1, 2], nms_score_threshold=2.0)
+    assert len(none) == 0 and none.get_field("labels").numel() == 0
+    some = _coder().decode_pyramid(loc, cls, sizes, [0, 1, 2], nms_score_threshold=0.5)
+    _same_detections(some, _coder().decode_pyramid_staged(loc, cls, sizes, [0, 1, 2], nms_score_threshold=0.5))
+    assert not some.has_field("transform_corners")
