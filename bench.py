@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--strong-classes", type=int, default=1000, help="global classes of the strong-scaling block (0 = skip)")
     ap.add_argument("--sustained-seconds", type=float, default=3.0, help="0 = skip the sustained block")
     ap.add_argument("--no-pipeline", action="store_true")
+    ap.add_argument("--wave-classes", type=int, default=0,
+                    help="run the five kernels class wave by class wave (this many classes per wave; 0 = all classes per kernel)")
     ap.add_argument("--cpu-sample-classes", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -406,6 +408,8 @@ def run_ours(args):
                         maps[rank * per + i] = own[i:i + 1]
                     self.sharded = bd.ClassShardedHead(maps, hc.create_os2d_head, gather=gather)
                     self.head = self.sharded.head
+            if args.wave_classes > 0:
+                self.head.max_planes_per_call = args.wave_classes * B
             self.handles = []
 
         def step(self, fm_d):
@@ -664,7 +668,8 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16 operands, fp32 accumulate (hi/lo-split weights)", "data": "synthetic",
-            "config": dict(workload_config(args, world), gather=(args.gather if world > 1 else None)),
+            "config": dict(workload_config(args, world), gather=(args.gather if world > 1 else None),
+                           wave_classes=(args.wave_classes or None)),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "parity": parity, "strong_c1000": strong, "pipeline": pipeline, "sustained": sustained}
     line.update(extra)

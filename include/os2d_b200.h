@@ -56,6 +56,12 @@ int os2d_pack_class_features_ragged(const float* const* map_ptrs, const int* hw,
 /* Image side (head.py:339): fm [B, D, N] fp32 -> packed [B, N, D] fp16 (values * 32 / (norm + 1e-5)).
  * inv_ws: workspace of B*N floats. */
 int os2d_pack_image_features(const float* fm, int B, int D, int N, float* inv_ws, void* packed, void* stream);
+/* Channels-last producer side (os2d/modeling/feature_extractor.py:23-72 + head.py:339): the
+ * backbone runs in NHWC, so its output rows [rows = B*H*W][D] are already in operand order.  x = a (+ b when b != NULL)
+ * (ReLU when relu != 0: the residual add + ReLU that ends layer3's last bottleneck is fused here), then the L2
+ * normalisation over D -> packed [rows, D] fp16 (x 32).  a / b: fp32 (is_half = 0) or fp16 (is_half = 1). */
+int os2d_pack_image_features_nhwc(const void* a, const void* b, int is_half, int relu, long long rows, int D, void* packed,
+                                  void* stream);
 
 /* ---- K1: correlation + ReLU/L2-norm epilogue (head.py:342-350, :650) ---------------------------------
  *   zvol   [B*C, 30, H*W, 8] fp16  centred/normalised correlation + DC side channels (conv1 operand)

@@ -35,6 +35,7 @@ SIGNATURES = {
     "os2d_pack_class_features_ragged": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
                                                  _c_void_p]),
     "os2d_pack_image_features": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
+    "os2d_pack_image_features_nhwc": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_ll, _c_int, _c_void_p, _c_void_p]),
     "os2d_correlate": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
                                 _c_void_p]),
     "os2d_conv_weight_blob_bytes": (ctypes.c_size_t, [_c_int, _c_int]),
@@ -129,6 +130,8 @@ def _first_cuda_tensor(obj, depth=0):
                 return t
     if hasattr(obj, "bbox_xyxy"):
         return _first_cuda_tensor(obj.bbox_xyxy, depth + 1)
+    if hasattr(obj, "packed"):                       # head.PackedFeatureMaps
+        return _first_cuda_tensor(obj.packed, depth + 1)
     return None
 
 

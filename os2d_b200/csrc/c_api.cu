@@ -3,6 +3,7 @@
 
 #include <atomic>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/os2d_b200.h"
@@ -17,6 +18,11 @@ void set_last_error(const char* what, cudaError_t e) {
   snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 void set_last_error_msg(const char* what) { snprintf(g_err, sizeof(g_err), "%s", what); }
+
+bool pdl_enabled() {
+  static const bool on = getenv("OS2D_B200_NO_PDL") == nullptr;
+  return on;
+}
 
 static std::atomic<unsigned long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -98,6 +104,12 @@ int os2d_pack_class_features_ragged(const float* const* map_ptrs, const int* hw,
 int os2d_pack_image_features(const float* fm, int B, int D, int N, float* inv_ws, void* packed, void* stream) {
   if (!fm || !inv_ws || !packed) return kErrBadArg;
   return launch_pack_image(fm, B, D, N, inv_ws, packed, static_cast<cudaStream_t>(stream));
+}
+
+int os2d_pack_image_features_nhwc(const void* a, const void* b, int is_half, int relu, long long rows, int D, void* packed,
+                                  void* stream) {
+  if (!a || !packed) return kErrBadArg;
+  return launch_pack_image_nhwc(a, b, is_half, relu, rows, D, packed, static_cast<cudaStream_t>(stream));
 }
 
 int os2d_correlate(const void* img_packed, const void* cls_packed, int B, int C, int D, int H, int W, void* zvol,

@@ -98,6 +98,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------
+// Every kernel of the head chain (image pack -> K1 -> conv1..3 -> K3) triggers its dependents first thing and waits for its
+// prerequisite right after its own set-up (barrier init, TMEM allocation, descriptor prefetch): the next kernel's CTAs are
+// placed and set up while the tail of the previous kernel is still running; no global memory is touched before the wait.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- TMA -------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -230,6 +237,30 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
 // host: tensor-map encoding through the driver entry point
 // ----------------------------------------------------------------------------------------------
 // rank <= 5; dims/strides fastest-first; strides[i] = byte stride of dim i+1 (rank-1 entries).
+// Launch with the programmatic-stream-serialization attribute (+ an optional cluster dimension).  OS2D_B200_NO_PDL=1 in
+// the environment falls back to plain stream order (A/B switch).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster_x); attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.attrs = n ? attr : nullptr; cfg.numAttrs = static_cast<unsigned>(n);
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                       const uint32_t* box, CUtensorMapSwizzle swizzle, CUtensorMapL2promotion promo);
 

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
   uint64_t* tempty = tfull + 2;            // one full/empty pair per strip accumulator
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&map_in);
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_plane = P.TY * P.TXP;
+  pdl_wait();          // the input volume is the previous kernel's output
 
   // Strip staggering: with 2 strips the first and the last 16-channel sub-chunk are issued strip by strip (their weight rows
   // are streamed twice), every other sub-chunk for both strips per weight load.  Strip 0's accumulator is therefore complete
@@ -401,8 +403,8 @@ static int launch_t(const ConvLayerDesc& L, const void* in_vol, const void* wblo
   P.out = out;
   OS2D_SET_MAX_DYN_SMEM(conv_kernel<KS>, G::SMEM_BYTES);
   const int grid = P.total_tiles < num_sms ? P.total_tiles : num_sms;
-  conv_kernel<KS><<<grid, THREADS, G::SMEM_BYTES, st>>>(map_in, P);
-  OS2D_AFTER_LAUNCH();
+  OS2D_CUDA_TRY(launch_pdl(conv_kernel<KS>, dim3(grid), dim3(THREADS), G::SMEM_BYTES, st, 1, map_in, P));
+  os2d::note_launch();
   return kOk;
 }
 

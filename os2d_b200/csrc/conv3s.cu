@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3s_kernel(const __grid_constan
   uint64_t* wfull = tempty + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) tma_prefetch_desc(&map_in);
   if (warp == 1 && lane == 0) {
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3s_kernel(const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_plane = P.TX * P.TY;
   const uint32_t b_bytes = 16u * P.NPAD * 16u;
+  pdl_wait();          // h2 is the previous kernel's output
 
   if (warp == 0) {
     if (lane == 0) {
@@ -209,8 +211,8 @@ int launch_conv3s(const void* h2_vol, const void* wblob, const float* bias, cons
   Pm.out = out;
   OS2D_SET_MAX_DYN_SMEM(conv3s_kernel, SMEM_BYTES);
   const int grid = Pm.total_tiles < num_sms ? Pm.total_tiles : num_sms;
-  conv3s_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(map_in, Pm);
-  OS2D_AFTER_LAUNCH();
+  OS2D_CUDA_TRY(launch_pdl(conv3s_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, map_in, Pm));
+  os2d::note_launch();
   return kOk;
 }
 

@@ -119,6 +119,7 @@ corr_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float2* part = reinterpret_cast<float2*>(smem + STAGES * K::STAGE_BYTES + 256);   // [2 acc stages][4 col groups][128 rows]
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = P.D / BK;
   const uint32_t rank = kTwoCta ? cluster_ctarank() : 0u;      // 0 = leader of the CTA pair
@@ -148,6 +149,7 @@ corr_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__
   if constexpr (kTwoCta) cluster_sync_all();     // barriers of both CTAs initialised before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // operands / output volumes may still be in use by the previous kernel of the stream
 
   if (warp == 0) {
     // ------------------------------ TMA producer (every CTA: its A tile + its part of the class tile) ----------
@@ -343,23 +345,15 @@ static int launch_t(const void* img_packed, const void* cls_packed, int B, int C
   P.zvol = reinterpret_cast<__half*>(zvol);
   P.rawvol = reinterpret_cast<__half*>(rawvol);
   OS2D_SET_MAX_DYN_SMEM(corr_kernel<kTwoCta>, K::SMEM_BYTES);
-  cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  unsigned grid;
   if (kTwoCta) {
     int pairs = num_sms / 2;
     if (pairs > P.total_tiles) pairs = P.total_tiles;
-    cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    grid = static_cast<unsigned>(2 * pairs);
   } else {
-    cfg.gridDim = dim3(static_cast<unsigned>(P.total_tiles < num_sms ? P.total_tiles : num_sms));
-    cfg.attrs = nullptr; cfg.numAttrs = 0;
+    grid = static_cast<unsigned>(P.total_tiles < num_sms ? P.total_tiles : num_sms);
   }
-  cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = K::SMEM_BYTES;
-  cfg.stream = st;
-  OS2D_CUDA_TRY(cudaLaunchKernelEx(&cfg, corr_kernel<kTwoCta>, map_img, map_cls, P));
+  OS2D_CUDA_TRY(launch_pdl(corr_kernel<kTwoCta>, dim3(grid), dim3(THREADS), K::SMEM_BYTES, st, kTwoCta ? 2 : 1, map_img, map_cls, P));
   os2d::note_launch();
   return kOk;
 }

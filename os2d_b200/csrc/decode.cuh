@@ -54,6 +54,20 @@ __device__ __forceinline__ bool iou_exceeds(const float4& bi, float iarea, const
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, jarea), inter));
   return static_cast<double>(ovr) > thr;
 }
+// Same decision with an early exit for boxes that do not intersect (the common case among NMS candidates): then
+// inter = +0, so ovr is 0 / (iarea + jarea) = +0 - or NaN when both areas are 0 - and `ovr > thr` is false for every
+// thr >= 0.  `nonneg_thr` (thr >= 0) is hoisted by the caller; with a negative threshold the full test always runs.
+__device__ __forceinline__ bool iou_exceeds_fast(const float4& bi, float iarea, const float4& bj, float jarea, double thr,
+                                                 bool nonneg_thr) {
+  const float xx1 = fmaxf(bi.x, bj.x), xx2 = fminf(bi.z, bj.z);
+  const float w = __fsub_rn(xx2, xx1);
+  const float yy1 = fmaxf(bi.y, bj.y), yy2 = fminf(bi.w, bj.w);
+  const float h = __fsub_rn(yy2, yy1);
+  if (nonneg_thr && (!(w > 0.f) || !(h > 0.f))) return false;
+  const float inter = __fmul_rn(fmaxf(0.f, w), fmaxf(0.f, h));
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, jarea), inter));
+  return static_cast<double>(ovr) > thr;
+}
 __device__ __forceinline__ float box_area(const float4& b) { return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)); }
 
 }  // namespace os2d

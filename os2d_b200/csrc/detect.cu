@@ -119,6 +119,7 @@ __device__ __forceinline__ void sort_desc(unsigned long long* k, int n) {
 __device__ __forceinline__ void greedy_nms(const float4* sb, uint8_t* supp, int m, double thr, float4* kb, float* ka, int* sh,
                                            int* bidx) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool nonneg = thr >= 0.0;
   int start = 0;
   while (start < m) {
     if (warp == 0) {
@@ -150,7 +151,7 @@ __device__ __forceinline__ void greedy_nms(const float4* sb, uint8_t* supp, int 
         bj.x = __shfl_sync(0xffffffffu, bi.x, j); bj.y = __shfl_sync(0xffffffffu, bi.y, j);
         bj.z = __shfl_sync(0xffffffffu, bi.z, j); bj.w = __shfl_sync(0xffffffffu, bi.w, j);
         const float aj = __shfl_sync(0xffffffffu, ai, j);
-        if (j < lane && lane < k && iou_exceeds(bj, aj, bi, thr)) smask |= 1u << j;
+        if (j < lane && lane < k && iou_exceeds_fast(bj, aj, bi, ai, thr, nonneg)) smask |= 1u << j;
       }
       unsigned kept = 0u;
       for (int i = 0; i < k; ++i) {
@@ -173,8 +174,9 @@ __device__ __forceinline__ void greedy_nms(const float4* sb, uint8_t* supp, int 
     for (int j = end + static_cast<int>(threadIdx.x); j < m; j += kThreads) {
       if (supp[j]) continue;
       const float4 bj = sb[j];
+      const float aj = box_area(bj);
       for (int q = 0; q < nk; ++q) {
-        if (iou_exceeds(kb[q], ka[q], bj, thr)) { supp[j] = 1; break; }
+        if (iou_exceeds_fast(kb[q], ka[q], bj, aj, thr, nonneg)) { supp[j] = 1; break; }
       }
     }
     __syncthreads();

@@ -28,6 +28,8 @@ int launch_pack_class(const float* maps, int C, int D, int h, int w, int normali
 int launch_pack_class_ragged(const float* const* map_ptrs, const int* hw, int C, int D, int normalize, float* cf32,
                              void* packed, cudaStream_t st);
 int launch_pack_image(const float* fm, int B, int D, int N, float* inv_ws, void* packed, cudaStream_t st);
+int launch_pack_image_nhwc(const void* a, const void* b, int is_half, int relu, long long rows, int D, void* packed,
+                           cudaStream_t st);
 
 // correlation GEMM + ReLU/L2norm/centering epilogue
 int launch_corr(const void* img_packed, const void* cls_packed, int B, int C, int D, int H, int W, void* zvol,

@@ -151,6 +151,8 @@ __global__ void __launch_bounds__(256) image_pack_kernel(const float* __restrict
   __shared__ float red[8][33];
   __shared__ float invs[32];
   __shared__ float tile[64][33];
+  pdl_launch_dependents();
+  pdl_wait();          // the packed operand / norm workspace may still be read by the previous image's kernels
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int b = blockIdx.y, p0 = blockIdx.x * 32, p = p0 + lane;
   const float* src = fm + static_cast<size_t>(b) * D * N;
@@ -191,6 +193,70 @@ __global__ void __launch_bounds__(256) image_pack_kernel(const float* __restrict
   }
 }
 
+// Channels-last variant ("backbone whose last layer writes the L2-normalised, MMA-ready feature
+// layout"): the backbone runs in torch.channels_last, so its output rows [B*N][D] already ARE the operand layout and no
+// transpose is needed.  One warp per location: x = a (+ b, ReLU: the residual add + ReLU that ends the last bottleneck of
+// layer3, os2d/modeling/feature_extractor.py:23-72, fused here), squared norm by shuffles, fp16 row = x * 32 / (|x| + 1e-5).
+// The whole row lives in registers (D <= 1024 per pass of 32 lanes x 32 values); a / b are fp32 or fp16.
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half* p) { return __half2float(*p); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) image_pack_nhwc_kernel(const T* __restrict__ a, const T* __restrict__ b, int relu,
+                                                               long long rows, int D, __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* pa = a + row * D;
+  const T* pb = b ? b + row * D : nullptr;
+  __half* po = out + row * D;
+  constexpr int kMaxPer = 32;                       // D <= 32 lanes * 2 * 32 = 2048
+  float2 v[kMaxPer];
+  float ss = 0.f;
+  const int pairs = D >> 1;                         // lane handles element pairs lane, lane + 32, ...
+#pragma unroll
+  for (int i = 0; i < kMaxPer; ++i) {
+    const int e = lane + 32 * i;
+    float x0 = 0.f, x1 = 0.f;
+    if (e < pairs) {
+      x0 = load_as_float(pa + 2 * e); x1 = load_as_float(pa + 2 * e + 1);
+      if (pb) { x0 += load_as_float(pb + 2 * e); x1 += load_as_float(pb + 2 * e + 1); }
+      if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+    }
+    v[i] = make_float2(x0, x1);
+    ss = fmaf(x0, x0, fmaf(x1, x1, ss));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float sc = kScaleFeat / (sqrtf(ss) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < kMaxPer; ++i) {
+    const int e = lane + 32 * i;
+    if (e < pairs) *reinterpret_cast<__half2*>(po + 2 * e) = __floats2half2_rn(v[i].x * sc, v[i].y * sc);
+  }
+}
+
+int launch_pack_image_nhwc(const void* a, const void* b, int is_half, int relu, long long rows, int D, void* packed,
+                           cudaStream_t st) {
+  if (rows <= 0 || D <= 0 || (D % 64) != 0 || D > 2048) return kErrBadArg;
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  if (is_half) {
+    OS2D_CUDA_TRY(launch_pdl(image_pack_nhwc_kernel<__half>, dim3(grid), dim3(256), 0, st, 1, reinterpret_cast<const __half*>(a),
+                             reinterpret_cast<const __half*>(b), relu, rows, D, reinterpret_cast<__half*>(packed)));
+  } else {
+    OS2D_CUDA_TRY(launch_pdl(image_pack_nhwc_kernel<float>, dim3(grid), dim3(256), 0, st, 1, reinterpret_cast<const float*>(a),
+                             reinterpret_cast<const float*>(b), relu, rows, D, reinterpret_cast<__half*>(packed)));
+  }
+  os2d::note_launch();
+  return kOk;
+}
+
 static int launch_pack_class_any(const float* maps, const float* const* map_ptrs, const int* hw, int h, int w, int C,
                                  int D, int normalize, float* cf32, void* packed, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
@@ -222,8 +288,9 @@ int launch_pack_class_ragged(const float* const* map_ptrs, const int* hw, int C,
 
 int launch_pack_image(const float* fm, int B, int D, int N, float* inv_ws, void* packed, cudaStream_t st) {
   if (B <= 0 || D <= 0 || N <= 0 || (D % 64) != 0) return kErrBadArg;
-  image_pack_kernel<<<dim3((N + 31) / 32, B), 256, 0, st>>>(fm, D, N, inv_ws, reinterpret_cast<__half*>(packed));
-  OS2D_AFTER_LAUNCH();
+  OS2D_CUDA_TRY(launch_pdl(image_pack_kernel, dim3((N + 31) / 32, B), dim3(256), 0, st, 1, fm, D, N, inv_ws,
+                           reinterpret_cast<__half*>(packed)));
+  os2d::note_launch();
   return kOk;
 }
 

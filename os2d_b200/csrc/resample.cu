@@ -57,6 +57,8 @@ template <typename Sink>
 __global__ void __launch_bounds__(128, 12) resample_kernel(const __half* __restrict__ raw, const float* __restrict__ params,
                                                         int P, int H, int W, int inverse, float stride_w,
                                                         float stride_h, float box_w, float box_h, const Sink sink) {
+  pdl_launch_dependents();
+  pdl_wait();          // params / raw are the previous kernels' outputs
   const int N = H * W;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   const int plane = blockIdx.y;
@@ -148,10 +150,10 @@ int launch_resample(const void* rawvol, const float* params, int planes, int P, 
   if (planes <= 0 || (P != 4 && P != 6) || H < 2 || W < 2) return kErrBadArg;
   const int N = H * W;
   const LocalSink sink{score, loc, corners, score_ps, loc_ps, corners_ps};
-  resample_kernel<LocalSink><<<dim3((N + 127) / 128, planes), 128, 0, st>>>(reinterpret_cast<const __half*>(rawvol), params,
-                                                                         P, H, W, inverse, stride_w, stride_h, box_w,
-                                                                         box_h, sink);
-  OS2D_AFTER_LAUNCH();
+  OS2D_CUDA_TRY(launch_pdl(resample_kernel<LocalSink>, dim3((N + 127) / 128, planes), dim3(128), 0, st, 1,
+                           reinterpret_cast<const __half*>(rawvol), params, P, H, W, inverse, stride_w, stride_h, box_w, box_h,
+                           sink));
+  os2d::note_launch();
   return kOk;
 }
 
@@ -161,10 +163,10 @@ int launch_resample_p2p(const void* rawvol, const float* params, int planes, int
   if (planes <= 0 || (P != 4 && P != 6) || H < 2 || W < 2 || n_peers <= 0 || !peers) return kErrBadArg;
   const int N = H * W;
   const PeerSink sink{peers, n_peers, score_off, loc_off, corners_off, plane_stride};
-  resample_kernel<PeerSink><<<dim3((N + 127) / 128, planes), 128, 0, st>>>(reinterpret_cast<const __half*>(rawvol), params,
-                                                                        P, H, W, inverse, stride_w, stride_h, box_w,
-                                                                        box_h, sink);
-  OS2D_AFTER_LAUNCH();
+  OS2D_CUDA_TRY(launch_pdl(resample_kernel<PeerSink>, dim3((N + 127) / 128, planes), dim3(128), 0, st, 1,
+                           reinterpret_cast<const __half*>(rawvol), params, P, H, W, inverse, stride_w, stride_h, box_w, box_h,
+                           sink));
+  os2d::note_launch();
   return kOk;
 }
 

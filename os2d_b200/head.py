@@ -32,6 +32,30 @@ LO_SCALE = 2048.0
 DC_CH = 225
 
 
+class PackedFeatureMaps:
+    """Image feature maps already in the head's operand layout: ``packed`` [B, H*W, D] fp16 = 32 * f / (||f|| + 1e-5)
+    (head.py:339), written by the channels-last backbone tail (os2d_b200.model.ResNetC4.forward_packed,
+    os2d_pack_image_features_nhwc).  ``Os2dHead.forward`` accepts it in place of the fp32 [B,D,H,W] tensor and skips its own
+    pack kernel; ``size(i)`` / ``shape`` / ``device`` mirror the tensor the reference would pass."""
+
+    def __init__(self, packed, height, width):
+        assert packed.dim() == 3 and packed.dtype == torch.float16 and packed.size(1) == height * width
+        self.packed = packed.contiguous()
+        self.shape = torch.Size((packed.size(0), packed.size(2), height, width))
+        self.device = packed.device
+        self.requires_grad = False
+
+    def size(self, i=None):
+        return self.shape if i is None else self.shape[i]
+
+    def __getitem__(self, idx):
+        """Image sub-batch (the evaluation iterator slices the batch dimension)."""
+        sub = self.packed[idx]
+        if sub.dim() == 2:
+            sub = sub.unsqueeze(0)
+        return PackedFeatureMaps(sub, self.shape[2], self.shape[3])
+
+
 def build_os2d_head_creator(do_simple_affine, is_cuda, use_inverse_geom_model, feature_map_stride,
                             feature_map_receptive_field):
     """Same factory as the reference (head.py:12-15)."""
@@ -488,11 +512,14 @@ class Os2dHead(nn.Module):
         inverse = 1 if self.aligner.use_inverse_geom_model else 0
         gen = self.box_grid_generator_image_level
 
-        fm = feature_maps.detach().to(dtype=torch.float32).contiguous()
-        img_packed = torch.empty(B, N, D, dtype=torch.float16, device=dev)
-        inv_ws = torch.empty(B, N, dtype=torch.float32, device=dev)
-        _cabi.check(self._timed("pack_image", lib.os2d_pack_image_features, _cabi.ptr(fm), B, D, N, _cabi.ptr(inv_ws),
-                                _cabi.ptr(img_packed), st), "os2d_pack_image_features")
+        if isinstance(feature_maps, PackedFeatureMaps):
+            img_packed = feature_maps.packed        # the producer already wrote the normalised fp16 operand
+        else:
+            fm = feature_maps.detach().to(dtype=torch.float32).contiguous()
+            img_packed = torch.empty(B, N, D, dtype=torch.float16, device=dev)
+            inv_ws = torch.empty(B, N, dtype=torch.float32, device=dev)
+            _cabi.check(self._timed("pack_image", lib.os2d_pack_image_features, _cabi.ptr(fm), B, D, N, _cabi.ptr(inv_ws),
+                                    _cabi.ptr(img_packed), st), "os2d_pack_image_features")
 
         if out_peers is not None:
             assert out_views is None, "out_views and out_peers are exclusive"

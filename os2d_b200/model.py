@@ -12,7 +12,8 @@ import torch
 import torch.nn as nn
 from torchvision.models.resnet import resnet50, resnet101
 
-from .head import build_os2d_head_creator
+from . import _cabi
+from .head import build_os2d_head_creator, PackedFeatureMaps
 from .structures import FeatureMapSize
 
 
@@ -35,6 +36,46 @@ class ResNetC4(nn.Module):
     def forward(self, x):
         x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
         return self.layer3(self.layer2(self.layer1(x)))
+
+    @torch.no_grad()
+    def forward_packed(self, x, half=False):
+        """Channels-last run of the same network whose LAST step - the residual add + ReLU that ends layer3's final
+        bottleneck (feature_extractor.py:23-72) - is fused with the head's image-side L2 normalisation (head.py:339) into
+        one kernel that writes the fp16 [B, H*W, D] GEMM operand (os2d_pack_image_features_nhwc).  The fp32 NCHW feature map,
+        its read-back by the head's pack kernel and the transpose never exist.  Eval mode only.  ``half=True`` additionally
+        runs the convolutions in fp16 (cuDNN tensor cores): that changes the backbone's numerics, which are outside the
+        parity-checked head path - the default keeps fp32."""
+        if self.training:
+            raise RuntimeError("forward_packed implements the evaluation regime (eval-mode BatchNorm) only")
+        if x.device.type != "cuda":
+            raise RuntimeError("os2d_b200 requires CUDA tensors (no CPU path)")
+        with torch.cuda.device(x.device):
+            ctx = torch.autocast("cuda", dtype=torch.float16) if half else torch.autocast("cuda", enabled=False)
+            with ctx:
+                x = x.contiguous(memory_format=torch.channels_last)
+                x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+                x = self.layer2(self.layer1(x))
+                for blk in list(self.layer3.children())[:-1]:
+                    x = blk(x)
+                blk = list(self.layer3.children())[-1]
+                assert blk.downsample is None, "the last bottleneck of layer3 has an identity shortcut in ResNet-50/101"
+                out = blk.relu(blk.bn1(blk.conv1(x)))
+                out = blk.relu(blk.bn2(blk.conv2(out)))
+                out = blk.bn3(blk.conv3(out))
+            B, D, H, W = out.shape
+            a = out.permute(0, 2, 3, 1)          # NHWC memory of a channels_last tensor: a contiguous [B,H,W,D] view
+            b = x.permute(0, 2, 3, 1)
+            if not a.is_contiguous() or not b.is_contiguous() or a.dtype != b.dtype:
+                a, b = a.contiguous(), b.to(a.dtype).contiguous()
+            packed = torch.empty(B, H * W, D, dtype=torch.float16, device=out.device)
+            lib = _cabi.load()
+            _cabi.check(lib.os2d_pack_image_features_nhwc(_cabi.ptr(a), _cabi.ptr(b), 1 if a.dtype == torch.float16 else 0, 1,
+                                                          B * H * W, D, _cabi.ptr(packed), _cabi.stream_ptr()),
+                        "os2d_pack_image_features_nhwc")
+            cur = torch.cuda.current_stream()
+            a.record_stream(cur)
+            b.record_stream(cur)
+        return PackedFeatureMaps(packed, H, W)
 
 
 class LabelFeatureExtractor(nn.Module):
@@ -101,12 +142,16 @@ class Os2dModel(nn.Module):
         with torch.no_grad():
             if feature_maps is None:
                 assert images is not None, "If feature_maps is None than images cannot be None"
-                feature_maps = self.net_feature_maps(images)
+                if getattr(self, "use_packed_feature_maps", False):
+                    feature_maps = self.net_feature_maps.forward_packed(images)
+                else:
+                    feature_maps = self.net_feature_maps(images)
             if class_head is None:
                 assert class_images is not None, "If class_conv_layer is None than class_images cannot be None"
                 class_head = self.os2d_head_creator.create_os2d_head(self.net_label_features(class_images))
             loc, cls, cls_detached, corners = self.apply_class_heads_to_feature_maps(feature_maps, class_head)
-        return loc, cls, cls_detached, FeatureMapSize(img=feature_maps), corners
+        fm_size = FeatureMapSize(w=feature_maps.size(3), h=feature_maps.size(2))
+        return loc, cls, cls_detached, fm_size, corners
 
     def get_feature_map_size(self, img_size):
         """The reference runs a dummy image through the backbone (model.py:98-120, 278-288); for the C4 ResNets

@@ -106,3 +106,62 @@ def test_eval_iterator_label_subset_and_decode():
                                 nms_iou_threshold=0.3, inverse_box_transforms=rev, transform_corners_pyramid=corners_p)
     assert len(dets) > 0 and dets.image_size == FeatureMapSize(w=352, h=256)
     assert set(dets.get_field("labels").tolist()) <= set(class_ids)
+
+
+class _EvalLoader(_Loader):
+    """+ the members the evaluation loop itself uses (os2d/engine/evaluate.py:35-36, 66, 104)."""
+
+    def __init__(self, *a, box_coder=None, annotations=None):
+        super().__init__(*a)
+        self.box_coder, self.annotations = box_coder, annotations
+
+    def get_name(self):
+        return "synthetic-eval"
+
+    def get_eval_scale(self):
+        return 1.0
+
+    def get_image_annotation_for_imageid(self, image_id):
+        return self.annotations[image_id]
+
+
+def test_evaluate_loop_metrics_and_detections_dump(tmp_path):
+    """os2d_b200.evaluate.evaluate: the inference side of the reference evaluate() (evaluate.py:20-174): losses keys, the
+    <dataset>_detections.pth dump format (evaluate.py:136-149) and mAP equal to the CPU oracle on the dumped detections."""
+    from os2d_b200.evaluate import evaluate
+    from os2d_b200.structures import FeatureMapSize, BoxList
+    from os2d_b200.box_coder import Os2dBoxCoder
+    from oracle import voc_oracle as vo
+    z = np.load(GOLDEN + "/eval_iterator.npz")
+    net = _model(z)
+    class_images, class_ids, pyramids = _inputs()
+    target = FeatureMapSize(w=352, h=256)
+    ann = {}
+    for k, image_id in enumerate([10, 11]):
+        gt = BoxList(torch.tensor([[20.0 + 30 * k, 30.0, 180.0, 170.0], [150.0, 60.0, 330.0, 240.0]]), target)
+        gt.add_field("labels", torch.tensor([4, 2 if k == 0 else 9]))
+        gt.add_field("difficult", torch.tensor([0, k]))
+        ann[image_id] = gt
+    coder = Os2dBoxCoder(0.5, 0.1, 0.8, 0.4, net.os2d_head_creator.box_grid_generator_image_level, net.get_feature_map_size)
+    loader = _EvalLoader(class_images, class_ids, pyramids, [10, 11], target, box_coder=coder, annotations=ann)
+    cfg = {"is_cuda": True,
+           "eval": {"batch_size": 2, "class_image_augmentation": "", "nms_iou_threshold": 0.3,
+                    "nms_score_threshold": float("-inf"), "mAP_iou_thresholds": [0.5, 0.3]},
+           "visualization": {"eval": {"path_to_save_detections": str(tmp_path)}}}
+    losses = evaluate(loader, net, cfg)
+    assert [k for k in losses] == ["mAP@0.50", "mAPw@0.50", "recall@0.50", "AP_joint_classes@0.50",
+                                   "mAP@0.30", "mAPw@0.30", "recall@0.30", "AP_joint_classes@0.30", "eval_time"]
+    data = torch.load(str(tmp_path / "synthetic-eval_detections.pth"))
+    assert sorted(data.keys()) == sorted(["image_ids", "boxes_xyxy", "labels", "scores", "gt_boxes_xyxy", "gt_labels", "gt_difficults"])
+    assert data["image_ids"] == [10, 11] and len(data["boxes_xyxy"]) == 2
+    assert all(not t.is_cuda for t in data["boxes_xyxy"] + data["scores"] + data["labels"])
+    assert data["boxes_xyxy"][0].shape[0] == data["scores"][0].shape[0] == data["labels"][0].shape[0] > 0
+    for thr in (0.5, 0.3):
+        ref = vo.eval_detection_voc([b.numpy() for b in data["boxes_xyxy"]], [l.numpy() for l in data["labels"]],
+                                    [s.numpy() for s in data["scores"]], [b.numpy() for b in data["gt_boxes_xyxy"]],
+                                    [l.numpy() for l in data["gt_labels"]], [d.numpy() for d in data["gt_difficults"]],
+                                    iou_thresh=thr)
+        assert abs(losses["mAP@{:0.2f}".format(thr)] - ref["map"]) < 1e-9
+        assert abs(losses["recall@{:0.2f}".format(thr)] - ref["recall"]) < 1e-9
+    with pytest.raises(NotImplementedError):
+        evaluate(loader, net, cfg, criterion=object())

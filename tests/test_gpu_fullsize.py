@@ -60,6 +60,71 @@ def test_config5_batch8_960px_and_v1_head():
     assert rel_to_max(corners[2:3, [3, 11]].cpu(), ocor) < TOL
 
 
+@pytest.mark.parametrize("side", [96, 112, 128])
+def test_config4_large_pyramid_levels_v1_head(side):
+    """configs[3]: the three largest levels of the 7-scale pyramid (1536 / 1792 / 2048 px -> 96^2 / 112^2 / 128^2 maps, up to
+    16 384 locations) with the V1 head (simplified affine P = 4, no inverse): a class subset against the oracle, class-chunk
+    invariance bit for bit, non-square variant of the level."""
+    C = 6
+    hc, cms, fm, tn = _setup(C, 1, side, True, False, 40 + side)
+    with torch.no_grad():
+        head = hc.create_os2d_head([cms[i:i + 1].cuda() for i in range(C)])
+        loc, rec, _, corners = head(fm.cuda())
+        head.max_planes_per_call = 4
+        head._cmax_cache.clear()
+        loc2, rec2, _, corners2 = head(fm.cuda())
+        # non-square level of the same scale (1280 x 960 image at this pyramid scale)
+        hh = side * 3 // 4
+        l3, r3, _, c3 = head(fm[:, :, :hh].contiguous().cuda())
+    torch.cuda.synchronize()
+    assert loc.shape == (1, C, 4, side, side)
+    assert torch.equal(loc, loc2) and torch.equal(rec, rec2) and torch.equal(corners, corners2)
+    sub = [1, 4]
+    cf = ho.prepare_class_features([cms[i:i + 1] for i in sub])
+    oloc, osc, ocor = ho.head_forward(cf, fm, tn, True, False, class_chunk=2)
+    assert rel_to_max(rec[:, sub].cpu(), osc) < TOL
+    assert rel_to_max(loc[:, sub].cpu(), oloc) < TOL
+    assert rel_to_max(corners[:, sub].cpu(), ocor) < TOL
+    oloc, osc, ocor = ho.head_forward(cf[:1], fm[:, :, :hh].contiguous(), tn, True, False, class_chunk=1)
+    assert rel_to_max(r3[:, sub[:1]].cpu(), osc) < TOL
+    assert rel_to_max(l3[:, sub[:1]].cpu(), oloc) < TOL
+    assert rel_to_max(c3[:, sub[:1]].cpu(), ocor) < TOL
+
+
+def test_config4_seven_level_run_head_to_detections():
+    """configs[3] end to end on the device: 7-level pyramid of feature maps (40..128) -> V1 head per level -> decode_pyramid
+    with the reference defaults (score threshold -inf, IoU 0.3: 52 740 candidates per class, chunked NMS to the fixpoint).
+    The fused two-launch post-processing equals the staged path bit for bit on the head's real outputs."""
+    from os2d_b200.box_coder import Os2dBoxCoder, make_resize_transform
+    from os2d_b200.structures import FeatureMapSize
+    sides = [40, 50, 64, 80, 96, 112, 128]
+    C = 4
+    hc, cms, _, tn = _setup(C, 1, 8, True, False, 77)
+    g = torch.Generator().manual_seed(78)
+    coder = Os2dBoxCoder(0.5, 0.1, 0.8, 0.4, hc.box_grid_generator_image_level,
+                         lambda sz: FeatureMapSize(w=-(-sz.w // 16), h=-(-sz.h // 16)))
+    tgt = FeatureMapSize(w=1280, h=1280)
+    loc_p, cls_p, cor_p = [], [], []
+    with torch.no_grad():
+        head = hc.create_os2d_head([cms[i:i + 1].cuda() for i in range(C)])
+        for s in sides:
+            fm = (torch.randn(1, 1024, s, s, generator=g) * 0.5 + 0.2).relu().cuda()
+            loc, rec, _, corners = head(fm)
+            loc_p.append(loc[0].view(C, 4, s * s))
+            cls_p.append(rec[0].view(C, s * s))
+            cor_p.append(corners[0].view(C, 8, s * s))
+        kw = dict(nms_score_threshold=float("-inf"), nms_iou_threshold=0.3,
+                  inverse_box_transforms=[make_resize_transform(tgt)] * 7, transform_corners_pyramid=cor_p)
+        sizes = [FeatureMapSize(w=16 * s, h=16 * s) for s in sides]
+        dets = coder.decode_pyramid(loc_p, cls_p, sizes, [3, 0, 2, 1], **kw)
+        staged = coder.decode_pyramid_staged(loc_p, cls_p, sizes, [3, 0, 2, 1], **kw)
+    assert len(dets) > 0 and dets.image_size == tgt
+    for f in ("scores", "labels", "transform_corners"):
+        assert torch.equal(dets.get_field(f), staged.get_field(f))
+    assert torch.equal(dets.bbox_xyxy, staged.bbox_xyxy)
+    assert torch.equal(dets.get_field("default_boxes").bbox_xyxy, staged.get_field("default_boxes").bbox_xyxy)
+
+
 def test_pyramid_decode_seven_levels_chunked():
     """configs[3] post-processing shape: 7 pyramid levels (52 740 anchors per class => chunked NMS).  Decoded boxes are
     compared with the oracle within tolerance; the NMS itself is checked on identical boxes (bit-exact) so that an ulp of
