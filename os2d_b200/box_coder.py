@@ -292,10 +292,9 @@ class Os2dBoxCoder:
                                             _cabi.ptr(boxes), _cabi.ptr(scores), _cabi.ptr(labels), _cabi.ptr(anchors),
                                             _cabi.ptr(corners), st)
             _cabi.check(rc, "os2d_gather_detections")
-        cur = torch.cuda.current_stream()
-        for t in alive + [cand, out_ids, keys, counts, offsets]:
-            if t is not None:
-                t.record_stream(cur)
+        # workspaces and fp32 copies stay referenced (`alive`, locals) until both launches are enqueued; the caching allocator
+        # hands their blocks out again in stream order on this same stream, so no record_stream is needed
+        del alive
         out = BoxList(boxes, out_size if out_size is not None else img_size_pyramid[0])
         out.add_field("scores", scores)
         out.add_field("default_boxes", BoxList(anchors, out.image_size))

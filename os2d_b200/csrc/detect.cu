@@ -20,6 +20,8 @@
 // them from their pairwise overlap bits, then all threads test the remaining boxes against the <= 32 boxes just kept.
 // This is the serial greedy algorithm exactly (a box is examined only after every earlier kept box has been applied to it)
 // with ~32x fewer block-wide barriers than one box per step.
+#include <cub/block/block_radix_sort.cuh>
+
 #include "common.cuh"
 #include "decode.cuh"
 #include "kernels.h"
@@ -33,6 +35,12 @@ constexpr size_t kBoxBytes = static_cast<size_t>(kChunk) * sizeof(float4);     /
 constexpr size_t kOrdBytes = static_cast<size_t>(kChunk) * sizeof(int);        // 40000
 constexpr size_t kSuppBytes = 10016;
 constexpr size_t kSmemBytes = kBoxBytes + kOrdBytes + kSuppBytes;
+
+// per-chunk order: stable descending radix sort on the 32 monotone score bits (CUB block primitive inside this kernel;
+// 10 items per thread cover a chunk of 10000), candidate positions as values - equal scores keep their list order
+constexpr int kItems = (kChunk + kThreads - 1) / kThreads;                      // 10
+using ChunkSort = cub::BlockRadixSort<unsigned int, kThreads, kItems, int>;
+static_assert(sizeof(ChunkSort::TempStorage) <= kBoxBytes, "sort scratch aliases the box tile");
 
 struct Split { int level; long long rem; };   // rem = view * N_l + anchor
 
@@ -115,8 +123,12 @@ __device__ __forceinline__ void sort_desc(unsigned long long* k, int n) {
   }
 }
 
-// greedy NMS of boxes sb[0..m) given in score-descending order; supp[i] = 1 for suppressed boxes
-__device__ __forceinline__ void greedy_nms(const float4* sb, uint8_t* supp, int m, double thr, float4* kb, float* ka, int* sh,
+// greedy NMS of boxes sb[0..m) given in score-descending order; supp[i] = 1 for suppressed boxes.
+// Per batch: (1) warp 0 collects the next <= 32 alive boxes; (2) warp j tests batch box j against the later batch boxes
+// (one overlap test per lane) and publishes the result as a ballot; (3) every thread resolves the greedy decisions of the
+// batch from the 32 ballots (a box is kept iff no earlier KEPT box of the batch overlaps it) and tests its own remaining
+// boxes against the kept ones.  Three block barriers per batch, no serial overlap loop.
+__device__ __forceinline__ void greedy_nms(const float4* sb, uint8_t* supp, int m, double thr, unsigned* ballots, int* sh,
                                            int* bidx) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool nonneg = thr >= 0.0;
@@ -141,42 +153,33 @@ __device__ __forceinline__ void greedy_nms(const float4* sb, uint8_t* supp, int 
           pos += 32;
         }
       }
-      __syncwarp();
-      const int k = cnt, end = min(pos, m);
-      const float4 bi = lane < k ? sb[bidx[lane]] : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float ai = box_area(bi);
-      unsigned smask = 0u;                     // bit j: box j of the batch (earlier in the order) overlaps this box
-      for (int j = 0; j < k; ++j) {
-        float4 bj;
-        bj.x = __shfl_sync(0xffffffffu, bi.x, j); bj.y = __shfl_sync(0xffffffffu, bi.y, j);
-        bj.z = __shfl_sync(0xffffffffu, bi.z, j); bj.w = __shfl_sync(0xffffffffu, bi.w, j);
-        const float aj = __shfl_sync(0xffffffffu, ai, j);
-        if (j < lane && lane < k && iou_exceeds_fast(bj, aj, bi, ai, thr, nonneg)) smask |= 1u << j;
-      }
-      unsigned kept = 0u;
-      for (int i = 0; i < k; ++i) {
-        const unsigned mi = __shfl_sync(0xffffffffu, smask, i);
-        if (!(mi & kept)) kept |= 1u << i;
-      }
-      if (lane < k) {
-        if ((kept >> lane) & 1u) {
-          const int slot = __popc(kept & ((1u << lane) - 1u));
-          kb[slot] = bi;
-          ka[slot] = ai;
-        } else {
-          supp[bidx[lane]] = 1;
-        }
-      }
-      if (lane == 0) { sh[0] = __popc(kept); sh[1] = end; }
+      if (lane == 0) { sh[0] = cnt; sh[1] = min(pos, m); }
     }
     __syncthreads();
-    const int nk = sh[0], end = sh[1];
+    const int k = sh[0], end = sh[1];
+    if (warp < k) {                            // row `warp` of the batch's overlap matrix: bit i = box warp overlaps box i (i > warp)
+      const float4 bj = sb[bidx[warp]];
+      bool ov = false;
+      if (lane > warp && lane < k) {
+        const float4 bi = sb[bidx[lane]];
+        ov = iou_exceeds_fast(bj, box_area(bj), bi, box_area(bi), thr, nonneg);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ov);
+      if (lane == 0) ballots[warp] = bal;
+    }
+    __syncthreads();
+    unsigned kept = 0u, dead = 0u;
+    for (int j = 0; j < k; ++j) {
+      if (!((dead >> j) & 1u)) { kept |= 1u << j; dead |= ballots[j]; }
+    }
+    if (threadIdx.x < k && !((kept >> threadIdx.x) & 1u)) supp[bidx[threadIdx.x]] = 1;      // batch members that lost
     for (int j = end + static_cast<int>(threadIdx.x); j < m; j += kThreads) {
       if (supp[j]) continue;
       const float4 bj = sb[j];
       const float aj = box_area(bj);
-      for (int q = 0; q < nk; ++q) {
-        if (iou_exceeds_fast(kb[q], ka[q], bj, aj, thr, nonneg)) { supp[j] = 1; break; }
+      for (unsigned rest = kept; rest; rest &= rest - 1u) {
+        const float4 bq = sb[bidx[__ffs(rest) - 1]];
+        if (iou_exceeds_fast(bq, box_area(bq), bj, aj, thr, nonneg)) { supp[j] = 1; break; }
       }
     }
     __syncthreads();
@@ -187,12 +190,10 @@ __device__ __forceinline__ void greedy_nms(const float4* sb, uint8_t* supp, int 
 __global__ void __launch_bounds__(kThreads, 1) label_nms_kernel(const DetectArgs A) {
   extern __shared__ __align__(16) uint8_t dsm[];
   float4* sb = reinterpret_cast<float4*>(dsm);
-  unsigned long long* skeys = reinterpret_cast<unsigned long long*>(dsm);       // aliases sb (used before the boxes are loaded)
   int* ord = reinterpret_cast<int*>(dsm + kBoxBytes);
   uint8_t* supp = dsm + kBoxBytes + kOrdBytes;
   __shared__ int wsum[33];
-  __shared__ float4 kb[32];
-  __shared__ float ka[32];
+  __shared__ unsigned ballots[32];
   __shared__ int sh[2];
   __shared__ int bidx[32];
   __shared__ int s_last;
@@ -237,17 +238,29 @@ __global__ void __launch_bounds__(kThreads, 1) label_nms_kernel(const DetectArgs
     int w = 0;
     for (int s = 0; s < n; s += kChunk) {
       const int m = min(kChunk, n - s);
-      for (int i = tid; i < m; i += kThreads) skeys[i] = make_key(score_of(A, cand[s + i]), i);
-      __syncthreads();
-      sort_desc(skeys, m);
-      for (int i = tid; i < m; i += kThreads) ord[i] = cand[s + key_pos(skeys[i])];
+      {
+        unsigned int keys[kItems];
+        int vals[kItems];
+#pragma unroll
+        for (int it = 0; it < kItems; ++it) {
+          const int i = tid * kItems + it;                      // blocked arrangement = list order (stability)
+          keys[it] = i < m ? mono_bits(score_of(A, cand[s + i])) : 0u;      // 0 sorts behind every real score
+          vals[it] = i;
+        }
+        ChunkSort(*reinterpret_cast<ChunkSort::TempStorage*>(dsm)).SortDescendingBlockedToStriped(keys, vals);
+#pragma unroll
+        for (int it = 0; it < kItems; ++it) {
+          const int r = it * kThreads + tid;                    // striped arrangement: rank r
+          if (r < m) ord[r] = cand[s + vals[it]];
+        }
+      }
       __syncthreads();
       for (int i = tid; i < m; i += kThreads) {
         sb[i] = decode_flat(A, ord[i]).box;
         supp[i] = 0;
       }
       __syncthreads();
-      greedy_nms(sb, supp, m, A.iou_thr, kb, ka, sh, bidx);
+      greedy_nms(sb, supp, m, A.iou_thr, ballots, sh, bidx);
       for (int i0 = 0; i0 < m; i0 += kThreads) {
         const int i = i0 + tid;
         const bool alive = i < m && !supp[i];
