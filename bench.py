@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-pipeline", action="store_true")
     ap.add_argument("--wave-classes", type=int, default=0,
                     help="run the five kernels class wave by class wave (this many classes per wave; 0 = all classes per kernel)")
+    ap.add_argument("--concurrent-corr", type=int, default=-1,
+                    help="SMs of the correlation kernel when it runs next to conv1 (0 = sequential kernels; -1 = library default)")
     ap.add_argument("--cpu-sample-classes", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -410,6 +412,8 @@ def run_ours(args):
                     self.head = self.sharded.head
             if args.wave_classes > 0:
                 self.head.max_planes_per_call = args.wave_classes * B
+            if args.concurrent_corr >= 0:
+                self.head.concurrent_corr_sms = args.concurrent_corr
             self.handles = []
 
         def step(self, fm_d):
@@ -503,6 +507,52 @@ def run_ours(args):
                     "note": "bytes are per rank; the replicated feature map is uploaded 1/N per rank and exchanged over NVLink"
                             if world > 1 else "feature map uploaded from pinned host memory every step"}
 
+        def e2e_detections(self, steps, warmup, coder, img):
+            """The user-level pipeline end to end with HOST buffers: feature map from pinned host memory (sharded upload at
+            N > 1) -> head -> decode + per-label NMS on this rank's labels -> gather of the survivors -> the detections
+            (boxes, scores, labels, default boxes, corners: what evaluate.py:118 moves to the CPU) copied to pinned host memory.
+            More work per step than `e2e` (it includes the post-processing), far fewer bytes back to the host."""
+            det = bd.ClassShardedDetector([None] * self.C_global, list(range(self.C_global)), lambda block: self.head, coder)
+            kw = dict(nms_score_threshold=float("-inf"), nms_iou_threshold=0.3)
+            up = bd.ShardedUpload(fm_host.shape, torch.float32, dev)
+            host_rows = torch.empty(400000, 18).pin_memory()
+            s_main = torch.cuda.current_stream()
+            fm_free = [None, None]
+            stats = {"rows": 0}
+
+            def run(n):
+                nxt = up.upload(fm_host, after_event=fm_free[0])
+                for i in range(n):
+                    fm_d, ev_in = nxt
+                    if i + 1 < n:                                  # prefetch: the next upload overlaps this step's kernels
+                        nxt = up.upload(fm_host, after_event=fm_free[(i + 1) % 2])
+                    s_main.wait_event(ev_in)
+                    with torch.no_grad():
+                        dets = det([fm_d[:1]], [img], **kw)
+                    fm_free[i % 2] = torch.cuda.Event()
+                    fm_free[i % 2].record(s_main)
+                    rows = torch.cat([dets.bbox_xyxy, dets.get_field("scores")[:, None],
+                                      dets.get_field("labels").to(torch.int32).view(torch.float32)[:, None],
+                                      dets.get_field("default_boxes").bbox_xyxy, dets.get_field("transform_corners")], dim=1)
+                    t = min(rows.shape[0], host_rows.shape[0])
+                    host_rows[:t].copy_(rows[:t], non_blocking=True)
+                    stats["rows"] = t
+                torch.cuda.synchronize()
+
+            run(max(2, warmup))
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            run(steps)
+            f1.record()
+            barrier()
+            ms = max_over_ranks(f0.elapsed_time(f1))
+            return {"value": self.C_global * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+                    "h2d_bytes_per_step": up.bytes_per_rank(), "d2h_bytes_per_step": stats["rows"] * 72,
+                    "detections": stats["rows"],
+                    "what": "host feature map -> head -> decode + per-label NMS (sharded by label) -> survivors gathered -> "
+                            "detections in pinned host memory; score threshold -inf; one image per step"}
+
         def parity(self):
             """N > 1: recompute the class block of rank (r + 1) % N on this rank and compare it bit for bit with the slice
             the gather delivered (driver-visible proof that the multi-GPU result equals the single-GPU one)."""
@@ -533,6 +583,37 @@ def run_ours(args):
     value = B * C * world * args.steps / (ms_total * 1e-3)
     e2e = weak.e2e(args.steps, args.warmup)
     parity = weak.parity()
+    e2e_det = None
+    if B == 1 and not args.no_pipeline:
+        try:
+            coder0 = Os2dBoxCoder(0.5, 0.1, 0.8, 0.4, hc.box_grid_generator_image_level,
+                                  lambda s: FeatureMapSize(w=-(-s.w // 16), h=-(-s.h // 16)))
+            e2e_det = weak.e2e_detections(args.steps, args.warmup, coder0, FeatureMapSize(w=fm_side * 16, h=fm_side * 16))
+        except Exception as e:   # noqa: BLE001
+            e2e_det = {"error": repr(e)}
+
+    # ---- host link: device -> host rate of one rank alone and of all ranks at once (the e2e download of the score maps is
+    # bound by the second figure on boxes whose GPUs share the host path) ----
+    host_link = None
+    if world > 1:
+        buf_d = torch.empty(32 * 1024 * 1024 // 4, device=dev)
+        buf_h = torch.empty(32 * 1024 * 1024 // 4).pin_memory()
+
+        def d2h_rate(active):
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            if active:
+                for _ in range(10):
+                    buf_h.copy_(buf_d, non_blocking=True)
+            t1.record()
+            barrier()
+            ms = max_over_ranks(t0.elapsed_time(t1) if active else 0.0)
+            return 10 * buf_d.numel() * 4 / (ms * 1e-3) / 1e9
+        alone = d2h_rate(rank == 0)
+        together = d2h_rate(True)
+        host_link = {"d2h_gbs_one_rank_alone": alone, "d2h_gbs_per_rank_all_ranks_at_once": together,
+                     "d2h_gbs_aggregate": together * world}
 
     # ---- sustained: the same step looped for >= args.sustained_seconds with its own clocks record ----
     sustained = None
@@ -669,9 +750,11 @@ def run_ours(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16 operands, fp32 accumulate (hi/lo-split weights)", "data": "synthetic",
             "config": dict(workload_config(args, world), gather=(args.gather if world > 1 else None),
-                           wave_classes=(args.wave_classes or None)),
+                           wave_classes=(args.wave_classes or None),
+                           concurrent_corr_sms=(args.concurrent_corr if args.concurrent_corr >= 0 else "library default")),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "parity": parity, "strong_c1000": strong, "pipeline": pipeline, "sustained": sustained}
+            "parity": parity, "strong_c1000": strong, "pipeline": pipeline, "sustained": sustained,
+            "e2e_detections": e2e_det, "host_link": host_link}
     line.update(extra)
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -69,6 +69,16 @@ int os2d_pack_image_features_nhwc(const void* a, const void* b, int is_half, int
 int os2d_correlate(const void* img_packed, const void* cls_packed, int B, int C, int D, int H, int W, void* zvol,
                    void* rawvol, void* stream);
 
+/* K1 and the first TransformNet layer side by side (stage-concurrent form of os2d_correlate + os2d_transform_conv(1)):
+ * the correlation kernel runs on `corr_sms` SMs (even, launched on aux_stream) and releases a per-plane completion count
+ * after every tile; conv1 runs on the other SMs (launched on `stream`) and acquires the count of a plane before its first TMA
+ * load of it, so it consumes the z volume while it is still in L2.  plane_flags: workspace of B*C uint32 (zeroed inside,
+ * stream-ordered).  On return `stream` also waits for the correlation kernel (raw volume complete).  Same results bit for
+ * bit as the two separate calls. */
+int os2d_correlate_conv1_concurrent(const void* img_packed, const void* cls_packed, int B, int C, int D, int H, int W, void* zvol,
+                                    void* rawvol, const void* w1blob, const float* alpha1, const float* beta1, void* h1,
+                                    unsigned int* plane_flags, int corr_sms, void* stream, void* aux_stream);
+
 /* ---- K2: TransformNet convolution layers (head.py:604-655) -------------------------------------------
  * layer 1: 225(+DC)->128 k7, BN+ReLU -> h1 [planes,16,H*W,8] fp16;
  * layer 2: 128->64 k5 (hi/lo weight rows), BN+ReLU -> h2 [planes,16,H*W,8] fp16 (chunks 0..7 value, 8..15 residual);

@@ -38,6 +38,9 @@ SIGNATURES = {
     "os2d_pack_image_features_nhwc": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_ll, _c_int, _c_void_p, _c_void_p]),
     "os2d_correlate": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
                                 _c_void_p]),
+    "os2d_correlate_conv1_concurrent": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
+                                                 _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p,
+                                                 _c_void_p]),
     "os2d_conv_weight_blob_bytes": (ctypes.c_size_t, [_c_int, _c_int]),
     "os2d_conv3_weight_blob_bytes": (ctypes.c_size_t, [_c_int]),
     "os2d_transform_conv": (_c_int, [_c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,

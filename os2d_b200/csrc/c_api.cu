@@ -120,6 +120,41 @@ int os2d_correlate(const void* img_packed, const void* cls_packed, int B, int C,
   return launch_corr(img_packed, cls_packed, B, C, D, H, W, zvol, rawvol, sms, static_cast<cudaStream_t>(stream));
 }
 
+// K1 and conv1 side by side: the correlation kernel runs on `corr_sms` SMs (stream `aux_stream`) and publishes every finished
+// plane; conv1 runs on the remaining SMs (stream `stream`) and consumes the planes as they complete, so the z volume is read
+// while it is still in L2 and K1 - off the critical path - is no longer bound by the chip-wide L2 -> SM delivery rate.
+int os2d_correlate_conv1_concurrent(const void* img_packed, const void* cls_packed, int B, int C, int D, int H, int W, void* zvol,
+                                    void* rawvol, const void* w1blob, const float* alpha1, const float* beta1, void* h1,
+                                    unsigned int* plane_flags, int corr_sms, void* stream, void* aux_stream) {
+  if (!img_packed || !cls_packed || !zvol || !rawvol || !w1blob || !alpha1 || !beta1 || !h1 || !plane_flags || !aux_stream)
+    return kErrBadArg;
+  const int sms = num_sms_cached();
+  if (sms <= 0) return kErrUnsupported;
+  if (corr_sms < 2 || (corr_sms & 1) || corr_sms > sms - 2) return kErrBadArg;
+  cudaStream_t st = static_cast<cudaStream_t>(stream), aux = static_cast<cudaStream_t>(aux_stream);
+  int dev = 0;
+  OS2D_CUDA_TRY(cudaGetDevice(&dev));
+  static cudaEvent_t ev_fork[kMaxDevices] = {}, ev_join[kMaxDevices] = {};
+  if (!ev_fork[dev]) {
+    OS2D_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
+    OS2D_CUDA_TRY(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
+  }
+  const int planes = B * C;
+  OS2D_CUDA_TRY(cudaMemsetAsync(plane_flags, 0, sizeof(unsigned int) * planes, st));
+  OS2D_CUDA_TRY(cudaEventRecord(ev_fork[dev], st));
+  OS2D_CUDA_TRY(cudaStreamWaitEvent(aux, ev_fork[dev], 0));
+  unsigned int target = 0;
+  int rc = launch_corr(img_packed, cls_packed, B, C, D, H, W, zvol, rawvol, corr_sms, aux, plane_flags, &target);
+  if (rc != kOk) return rc;
+  OS2D_CUDA_TRY(cudaEventRecord(ev_join[dev], aux));
+  ConvLayerDesc L;
+  L.lo_scale = 1.0f / 2048.0f; L.ksize = 7; L.in_chunks16 = kCorrPad / 16; L.out_real = 128; L.mode = 0;
+  rc = launch_conv(L, zvol, w1blob, alpha1, beta1, h1, planes, H, W, sms - corr_sms, st, plane_flags, target);
+  if (rc != kOk) return rc;
+  OS2D_CUDA_TRY(cudaStreamWaitEvent(st, ev_join[dev], 0));     // raw volume (K3's input) and K1 itself are complete
+  return kOk;
+}
+
 size_t os2d_conv_weight_blob_bytes(int ksize, int in_chunks16) { return conv_weight_blob_bytes(ksize, in_chunks16); }
 size_t os2d_conv3_weight_blob_bytes(int P) { return conv3s_weight_blob_bytes(P); }
 

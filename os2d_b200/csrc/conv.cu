@@ -55,6 +55,8 @@ struct Params {
   const float* beta;
   void* out;
   int n_double;       // tiles [0, n_double) are 2-strip tiles; the rest are the last partial wave split in 1-strip tiles
+  const unsigned int* wait_flags;   // optional: per-plane completion counters of the kernel that is WRITING the input volume
+  unsigned int wait_target;         //           concurrently on other SMs (stage-concurrent K1 -> conv1); plane ready at >= target
 };
 
 struct TileInfo { int plane, y0, x0, rows, nstrips; };
@@ -127,11 +129,24 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
     if (lane == 0) {
       int hs = 0; uint32_t hph = 0;
       int ws = 0; uint32_t wph = 0;
+      int ready_plane = -1;
       for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
         const TileInfo ti = decode_tile(P, t);
         if (ti.nstrips == 0) continue;
         const int plane = ti.plane, y0 = ti.y0, x0 = ti.x0;
         const bool stag = ti.nstrips == 2 && P.nsub >= 2;
+        if (P.wait_flags != nullptr && plane > ready_plane) {
+          // the producing kernel runs concurrently: acquire the plane's completion count, then order the generic-proxy
+          // acquire before the async-proxy (TMA) reads.  Bounded wait (~4 s) so that a scheduling accident cannot hang the GPU.
+          const unsigned int* f = P.wait_flags + plane;
+          const long long t0 = clock64();
+          while (ld_acquire_gpu_u32(f) < P.wait_target) {
+            __nanosleep(200);
+            if (clock64() - t0 > (1ll << 33)) break;
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");
+          ready_plane = plane;
+        }
         for (int sc = 0; sc < P.nsub; ++sc) {
           mbar_wait(&hempty[hs], hph ^ 1);
           mbar_expect_tx(&hfull[hs], G::HALO_BYTES);
@@ -345,7 +360,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
 
 template <int KS>
 static int launch_t(const ConvLayerDesc& L, const void* in_vol, const void* wblob, const float* alpha,
-                    const float* beta, void* out, int planes, int H, int W, int num_sms, cudaStream_t st) {
+                    const float* beta, void* out, int planes, int H, int W, int num_sms, cudaStream_t st,
+                    const unsigned int* wait_flags, unsigned int wait_target) {
   using G = Geo<KS>;
   const int in_chunks8 = L.in_chunks16 * 2;
   CUtensorMap map_in;
@@ -401,6 +417,8 @@ static int launch_t(const ConvLayerDesc& L, const void* in_vol, const void* wblo
   P.alpha = alpha;
   P.beta = beta;
   P.out = out;
+  P.wait_flags = wait_flags;
+  P.wait_target = wait_target;
   OS2D_SET_MAX_DYN_SMEM(conv_kernel<KS>, G::SMEM_BYTES);
   const int grid = P.total_tiles < num_sms ? P.total_tiles : num_sms;
   OS2D_CUDA_TRY(launch_pdl(conv_kernel<KS>, dim3(grid), dim3(THREADS), G::SMEM_BYTES, st, 1, map_in, P));
@@ -415,11 +433,12 @@ size_t conv_weight_blob_bytes(int ksize, int in_chunks16) {
 }
 
 int launch_conv(const ConvLayerDesc& L, const void* in_vol, const void* wblob, const float* alpha, const float* beta,
-                void* out, int planes, int H, int W, int num_sms, cudaStream_t st) {
+                void* out, int planes, int H, int W, int num_sms, cudaStream_t st, const unsigned int* wait_flags,
+                unsigned int wait_target) {
   if (planes <= 0 || H <= 0 || W <= 0 || L.in_chunks16 <= 0 || L.mode < 0 || L.mode > 1) return kErrBadArg;
   if ((static_cast<uint64_t>(16) * W) % 16 != 0) return kErrBadArg;
-  if (L.ksize == 7) return conv::launch_t<7>(L, in_vol, wblob, alpha, beta, out, planes, H, W, num_sms, st);
-  if (L.ksize == 5) return conv::launch_t<5>(L, in_vol, wblob, alpha, beta, out, planes, H, W, num_sms, st);
+  if (L.ksize == 7) return conv::launch_t<7>(L, in_vol, wblob, alpha, beta, out, planes, H, W, num_sms, st, wait_flags, wait_target);
+  if (L.ksize == 5) return conv::launch_t<5>(L, in_vol, wblob, alpha, beta, out, planes, H, W, num_sms, st, wait_flags, wait_target);
   return kErrUnsupported;
 }
 

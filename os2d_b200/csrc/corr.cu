@@ -50,6 +50,7 @@ struct Params {
   int total_tiles;          // 1-CTA: planes * MT tiles; 2-CTA: planes * ceil(MT / 2) tile pairs
   __half* zvol;
   __half* rawvol;
+  unsigned int* plane_done;   // optional: += 1 per finished (CTA, tile) of a plane, released at gpu scope (stage-concurrent conv1)
 };
 
 // ---- cluster helpers (2-CTA variant) ----
@@ -117,6 +118,7 @@ corr_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* tile_cnt = tmem_slot + 2;      // [2]: epilogue warps that have finished the tile in accumulator stage 0 / 1
   float2* part = reinterpret_cast<float2*>(smem + STAGES * K::STAGE_BYTES + 256);   // [2 acc stages][4 col groups][128 rows]
 
   pdl_launch_dependents();
@@ -134,6 +136,7 @@ corr_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kTwoCta ? 32 : 16); }
+    tile_cnt[0] = 0u; tile_cnt[1] = 0u;
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -297,9 +300,19 @@ corr_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__
           *reinterpret_cast<uint4*>(zbase + static_cast<size_t>(2 * cb + 1) * P.N * 8) = make_uint4(zq[4], zq[5], zq[6], zq[7]);
         }
       }
+      if (P.plane_done != nullptr) __threadfence();     // this thread's z / raw stores are visible at gpu scope
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
+        if (P.plane_done != nullptr) {
+          // the 16th epilogue warp of this CTA to finish the tile publishes it (fence + relaxed RMW = release at gpu scope,
+          // cumulative over the other warps' fenced stores through the shared-memory counter)
+          if (atomicAdd(&tile_cnt[as], 1u) == 15u) {
+            tile_cnt[as] = 0u;
+            __threadfence();
+            atomicAdd(P.plane_done + plane, 1u);
+          }
+        }
         if constexpr (kTwoCta) mbar_arrive_remote(tempty_remote[as]);   // the leader's barrier collects both CTAs
         else mbar_arrive(&tempty[as]);
       }
@@ -319,7 +332,7 @@ corr_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__
 
 template <bool kTwoCta>
 static int launch_t(const void* img_packed, const void* cls_packed, int B, int C, int D, int N, void* zvol, void* rawvol,
-                    int num_sms, cudaStream_t st) {
+                    int num_sms, unsigned int* plane_done, unsigned int* signals_per_plane, cudaStream_t st) {
   using K = Cfg<kTwoCta>;
   CUtensorMap map_img, map_cls;
   {
@@ -344,6 +357,8 @@ static int launch_t(const void* img_packed, const void* cls_packed, int B, int C
   P.total_tiles = B * C * (kTwoCta ? (P.MT + 1) / 2 : P.MT);
   P.zvol = reinterpret_cast<__half*>(zvol);
   P.rawvol = reinterpret_cast<__half*>(rawvol);
+  P.plane_done = plane_done;
+  if (signals_per_plane) *signals_per_plane = static_cast<unsigned int>(kTwoCta ? 2 * ((P.MT + 1) / 2) : P.MT);
   OS2D_SET_MAX_DYN_SMEM(corr_kernel<kTwoCta>, K::SMEM_BYTES);
   unsigned grid;
   if (kTwoCta) {
@@ -361,14 +376,15 @@ static int launch_t(const void* img_packed, const void* cls_packed, int B, int C
 }  // namespace corr
 
 int launch_corr(const void* img_packed, const void* cls_packed, int B, int C, int D, int H, int W, void* zvol,
-                void* rawvol, int num_sms, cudaStream_t st) {
+                void* rawvol, int num_sms, cudaStream_t st, unsigned int* plane_done, unsigned int* signals_per_plane) {
   using namespace corr;
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D % BK != 0) return kErrBadArg;
   const int N = H * W;
   // variant selection: 2-CTA unless OS2D_B200_CORR_1CTA is set (A/B switch; both are tested)
   static const bool one_cta = getenv("OS2D_B200_CORR_1CTA") != nullptr;
-  if (one_cta || num_sms < 2) return launch_t<false>(img_packed, cls_packed, B, C, D, N, zvol, rawvol, num_sms, st);
-  return launch_t<true>(img_packed, cls_packed, B, C, D, N, zvol, rawvol, num_sms, st);
+  if (one_cta || num_sms < 2)
+    return launch_t<false>(img_packed, cls_packed, B, C, D, N, zvol, rawvol, num_sms, plane_done, signals_per_plane, st);
+  return launch_t<true>(img_packed, cls_packed, B, C, D, N, zvol, rawvol, num_sms, plane_done, signals_per_plane, st);
 }
 
 }  // namespace os2d

@@ -32,8 +32,11 @@ int launch_pack_image_nhwc(const void* a, const void* b, int is_half, int relu, 
                            cudaStream_t st);
 
 // correlation GEMM + ReLU/L2norm/centering epilogue
+// plane_done (optional): per-plane completion counters for a concurrently running conv1 (see os2d_correlate_conv1_concurrent);
+// signals_per_plane (optional, host): how many increments complete a plane
 int launch_corr(const void* img_packed, const void* cls_packed, int B, int C, int D, int H, int W, void* zvol,
-                void* rawvol, int num_sms, cudaStream_t st);
+                void* rawvol, int num_sms, cudaStream_t st, unsigned int* plane_done = nullptr,
+                unsigned int* signals_per_plane = nullptr);
 
 // implicit-GEMM convolution layer of the TransformNet.  layer: 1, 2, 3
 struct ConvLayerDesc {
@@ -45,8 +48,11 @@ struct ConvLayerDesc {
                       //    as two planes sets: chunks 0..7 = fp16 value, chunks 8..15 = fp16 residual
   float lo_scale;     // factor applied to the lo-row accumulator before adding (2^-11) in modes 1/2
 };
+// wait_flags (optional): the producer of a tile polls wait_flags[plane] >= wait_target (acquire, gpu scope) before its first
+// load of that plane - the input volume is being written by a kernel running concurrently on other SMs
 int launch_conv(const ConvLayerDesc& L, const void* in_vol, const void* wblob, const float* alpha, const float* beta,
-                void* out, int planes, int H, int W, int num_sms, cudaStream_t st);
+                void* out, int planes, int H, int W, int num_sms, cudaStream_t st, const unsigned int* wait_flags = nullptr,
+                unsigned int wait_target = 0);
 
 int launch_resample(const void* rawvol, const float* params, int planes, int P, int H, int W, int inverse,
                     float stride_w, float stride_h, float box_w, float box_h, float* score, float* loc,

@@ -110,8 +110,9 @@ class SymmetricSlots:
         optional ``fill()`` (e.g. an H2D copy of this rank's part), push this rank's part to every peer, barrier (all
         parts have landed everywhere).  Returns the event that marks slot k complete on this rank."""
         with torch.cuda.stream(self.stream):
-            if after_event is not None:
-                self.stream.wait_event(after_event)
+            for ev in (after_event if isinstance(after_event, (list, tuple)) else [after_event]):
+                if ev is not None:
+                    self.stream.wait_event(ev)
             self.barrier(k)
             if fill is not None:
                 fill()
@@ -133,6 +134,8 @@ class GatherHandle:
         self.owner, self.slot, self.pending, self.B, self.H, self.W = owner, slot, pending, B, H, W
 
     def wait(self):
+        if isinstance(self.pending, str):           # exchange still deferred (see ClassShardedHead.submit): start it now
+            self.owner._flush_deferred()
         p = self.pending
         if p is not None:
             if isinstance(p, torch.cuda.Event):
@@ -174,6 +177,10 @@ class ClassShardedHead:
         self.depth = depth
         self._rings = {}
         self._step = 0
+        # copy-engine mode: the pushes of image i are enqueued only once K1 of image i+1 has been launched (and wait for it),
+        # so the inbound NVLink writes overlap the tensor-bound conv1 instead of the L2-delivery-bound correlation kernel
+        self.defer_exchange = True
+        self._deferred = None
 
     # ---- buffers: allocated once per (B, N) shape (collective for the symmetric modes), reused by every call ----
     def _ring(self, B, N, device):
@@ -206,6 +213,8 @@ class ClassShardedHead:
         k = self._step % self.depth
         self._step += 1
         slot = ring["buffer"][k]
+        if self._deferred is not None and (self._deferred["ring"] is not ring or self._deferred["k"] == k):
+            self._flush_deferred()
         prev = ring["pending"][k]
         if prev is not None:                       # the previous gather into this slot must be over before it is rewritten
             if isinstance(prev, torch.cuda.Event):
@@ -225,29 +234,50 @@ class ClassShardedHead:
                 slots.barrier(k)
             slots.barrier(k)                                              # every rank's stores have landed everywhere
             return GatherHandle(self, slot, None, B, H, W)
+        def after_corr():
+            if self._deferred is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                self._flush_deferred(ev)
+
         if self.head is not None:
             s_v, l_v, c_v = local_views(slot, self.rank)
             if getattr(self.head, "supports_out_views", False):
                 # the resample kernel writes straight into this rank's slice of the gather buffer (no staging copy)
-                self.head(feature_maps, out_views=(s_v[:, :n], l_v[:, :n], c_v[:, :n]))
+                self.head(feature_maps, out_views=(s_v[:, :n], l_v[:, :n], c_v[:, :n]), _after_corr=after_corr)
             else:
                 loc, score, _, corners = self.head(feature_maps)
                 s_v[:, :n].copy_(score.reshape(B, n, 1, N))
                 l_v[:, :n].copy_(loc.reshape(B, n, 4, N))
                 c_v[:, :n].copy_(corners.reshape(B, n, 8, N))
+        after_corr()                               # no-op when the head already triggered it
         pending = None
         if self.world > 1:
             if mode == "copy_engine":
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream())
+                if self.defer_exchange:
+                    handle = GatherHandle(self, slot, "deferred", B, H, W)
+                    self._deferred = {"ring": ring, "k": k, "ev_head": ev, "handle": handle}
+                    return handle
                 pending = ring["slots"].exchange(k, ev)
             else:
                 pending = all_gather_outputs(slot, self.group, async_op=True)
             ring["pending"][k] = pending
         return GatherHandle(self, slot, pending, B, H, W)
 
+    def _flush_deferred(self, extra_event=None):
+        d = self._deferred
+        if d is None:
+            return
+        self._deferred = None
+        ev = d["ring"]["slots"].exchange(d["k"], [d["ev_head"], extra_event])
+        d["ring"]["pending"][d["k"]] = ev
+        d["handle"].pending = ev
+
     def drain(self):
         """Wait (stream-level) for every gather still in flight."""
+        self._flush_deferred()
         for ring in self._rings.values():
             for k, p in enumerate(ring["pending"]):
                 if p is not None:

@@ -14,6 +14,7 @@ fallback path in this package.
 """
 import ctypes
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -162,19 +163,32 @@ def _require_inference(t, module):
         raise RuntimeError("os2d_b200 requires CUDA tensors (no CPU path)")
 
 
+_AUX_STREAMS = {}
+
+
+def _aux_stream(dev):
+    """Side stream of the stage-concurrent correlation kernel, one per device."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _AUX_STREAMS:
+        _AUX_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _AUX_STREAMS[key]
+
+
 @_cabi.on_device_of
-def run_transform_convs(pw, P, zvol, planes, H, W, timed=None):
-    """z volume [planes,30,N,8] -> parameters [planes,P,N] through the three conv kernels (os2d_transform_conv 1..3)."""
+def run_transform_convs(pw, P, zvol, planes, H, W, timed=None, h1=None):
+    """z volume [planes,30,N,8] -> parameters [planes,P,N] through the three conv kernels (os2d_transform_conv 1..3);
+    with ``h1`` given, layer 1 has already run (os2d_correlate_conv1_concurrent)."""
     lib = _cabi.load()
     st = _cabi.stream_ptr()
     dev = zvol.device
     N = H * W
     call = timed if timed is not None else (lambda name, fn, *a: fn(*a))
-    h1 = torch.empty(planes, 16, N, 8, dtype=torch.float16, device=dev)
     h2 = torch.empty(planes, 16, N, 8, dtype=torch.float16, device=dev)
     params = torch.empty(planes, P, N, dtype=torch.float32, device=dev)
-    _cabi.check(call("conv1", lib.os2d_transform_conv, 1, 128, _cabi.ptr(zvol), _cabi.ptr(pw["w1"]), _cabi.ptr(pw["alpha1"]),
-                     _cabi.ptr(pw["beta1"]), _cabi.ptr(h1), planes, H, W, st), "os2d_transform_conv(1)")
+    if h1 is None:
+        h1 = torch.empty(planes, 16, N, 8, dtype=torch.float16, device=dev)
+        _cabi.check(call("conv1", lib.os2d_transform_conv, 1, 128, _cabi.ptr(zvol), _cabi.ptr(pw["w1"]), _cabi.ptr(pw["alpha1"]),
+                         _cabi.ptr(pw["beta1"]), _cabi.ptr(h1), planes, H, W, st), "os2d_transform_conv(1)")
     _cabi.check(call("conv2", lib.os2d_transform_conv, 2, 64, _cabi.ptr(h1), _cabi.ptr(pw["w2"]), _cabi.ptr(pw["alpha2"]),
                      _cabi.ptr(pw["beta2"]), _cabi.ptr(h2), planes, H, W, st), "os2d_transform_conv(2)")
     _cabi.check(call("conv3", lib.os2d_transform_conv, 3, P, _cabi.ptr(h2), _cabi.ptr(pw["w3"]), _cabi.ptr(pw["alpha3"]),
@@ -429,6 +443,7 @@ class Os2dHead(nn.Module):
         self.class_pool_mask = mask / mask.sum(dim=(2, 3), keepdim=True)     # head.py:295-302
         self.aligner = aligner
         self.max_planes_per_call = 4096
+        self.concurrent_corr_sms = None  # see _concurrent_corr_sms
         self.workspace_bytes = None      # byte bound of the per-call workspace; None = half of the free device memory
         self._cmax_cache = {}
         self.supports_out_views = True
@@ -449,6 +464,7 @@ class Os2dHead(nn.Module):
         sub.class_pool_mask = self.class_pool_mask.index_select(0, idx)
         sub.aligner = self.aligner
         sub.max_planes_per_call = self.max_planes_per_call
+        sub.concurrent_corr_sms = self.concurrent_corr_sms
         sub.workspace_bytes = self.workspace_bytes
         sub._cmax_cache = {}
         sub.supports_out_views = True
@@ -470,6 +486,17 @@ class Os2dHead(nn.Module):
             self._cmax_cache[key] = max(1, min(self.max_planes_per_call, int(budget) // per_plane) // B)
         return self._cmax_cache[key]
 
+    def _concurrent_corr_sms(self, planes, N):
+        """SMs given to the correlation kernel when it runs NEXT TO conv1 (0 = one after the other).  ``concurrent_corr_sms``:
+        None = environment OS2D_B200_CONCURRENT_CORR (default off), else the even SM count.  Only for problems with enough
+        planes to keep both kernels busy."""
+        n = self.concurrent_corr_sms
+        if n is None:
+            n = int(os.environ.get("OS2D_B200_CONCURRENT_CORR", "0") or 0)
+        if n <= 0 or planes < 8 or planes * N < 40000:
+            return 0
+        return n & ~1
+
     def _timed(self, name, fn, *a):
         if self.profile_events is None:
             return fn(*a)
@@ -481,7 +508,7 @@ class Os2dHead(nn.Module):
         return rc
 
     @_cabi.on_device_of
-    def forward(self, feature_maps, out_views=None, out_peers=None, _before_resample=None):
+    def forward(self, feature_maps, out_views=None, out_peers=None, _before_resample=None, _after_corr=None):
         """feature_maps [B,D,H,W] -> (loc [B,C,4,H,W], rec [B,C,1,H,W], rec_transform_detached (same tensor under
         no-grad, head.py:400-402), corners [B,C,8,H,W]).  ``out_views`` (extension, default None): (score, loc, corners)
         strided views [B,C,k,H*W] to write into instead of fresh tensors; the call then returns None.
@@ -544,9 +571,23 @@ class Os2dHead(nn.Module):
             zvol = torch.empty(planes, Z_CHUNKS, N, 8, dtype=torch.float16, device=dev)
             rawvol = torch.empty(planes, CORR_CH, N, dtype=torch.float16, device=dev)
             cls = self._class_packed[c0:c0 + cc]
-            _cabi.check(self._timed("corr", lib.os2d_correlate, _cabi.ptr(img_packed), _cabi.ptr(cls), B, cc, D, H, W,
-                                    _cabi.ptr(zvol), _cabi.ptr(rawvol), st), "os2d_correlate")
-            params = run_transform_convs(pw, P, zvol, planes, H, W, timed=self._timed)
+            corr_sms = self._concurrent_corr_sms(planes, N)
+            if corr_sms:
+                # K1 on `corr_sms` SMs next to conv1 on the others: conv1 consumes every plane as soon as K1 has released it
+                h1 = torch.empty(planes, 16, N, 8, dtype=torch.float16, device=dev)
+                flags = torch.empty(planes, dtype=torch.int32, device=dev)
+                _cabi.check(self._timed("corr+conv1", lib.os2d_correlate_conv1_concurrent, _cabi.ptr(img_packed), _cabi.ptr(cls),
+                                        B, cc, D, H, W, _cabi.ptr(zvol), _cabi.ptr(rawvol), _cabi.ptr(pw["w1"]),
+                                        _cabi.ptr(pw["alpha1"]), _cabi.ptr(pw["beta1"]), _cabi.ptr(h1), _cabi.ptr(flags), corr_sms,
+                                        st, ctypes.c_void_p(_aux_stream(dev).cuda_stream)), "os2d_correlate_conv1_concurrent")
+                params = run_transform_convs(pw, P, zvol, planes, H, W, timed=self._timed, h1=h1)
+            else:
+                _cabi.check(self._timed("corr", lib.os2d_correlate, _cabi.ptr(img_packed), _cabi.ptr(cls), B, cc, D, H, W,
+                                        _cabi.ptr(zvol), _cabi.ptr(rawvol), st), "os2d_correlate")
+                params = run_transform_convs(pw, P, zvol, planes, H, W, timed=self._timed)
+            if _after_corr is not None:          # hook of os2d_b200.dist: K1 (of the first chunk) has been launched
+                _after_corr()
+                _after_corr = None
             if _before_resample is not None:
                 _before_resample()
                 _before_resample = None

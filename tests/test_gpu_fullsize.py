@@ -169,3 +169,23 @@ def test_pyramid_decode_seven_levels_chunked():
         # and the end-to-end detections of this label agree with the oracle up to decisions an ulp could flip
         n_dets = int((dets.get_field("labels") == lab).sum())
         assert abs(n_dets - keep.shape[0]) <= max(3, keep.shape[0] // 100)
+
+
+@pytest.mark.parametrize("corr_sms", [16, 24])
+def test_stage_concurrent_corr_conv1_is_bit_identical(corr_sms):
+    """K1 running NEXT TO conv1 (os2d_correlate_conv1_concurrent: K1 on `corr_sms` SMs releases each finished plane, conv1 on the
+    other SMs acquires it before its first TMA load) must not change a bit relative to the two kernels one after the other."""
+    hc, cms, fm, tn = _setup(30, 1, 80, False, True, 11)
+    with torch.no_grad():
+        head = hc.create_os2d_head([cms[i:i + 1].cuda() for i in range(30)])
+        head.concurrent_corr_sms = 0
+        loc, rec, _, corners = head(fm.cuda())
+        head.concurrent_corr_sms = corr_sms
+        for _ in range(3):                      # repeated: flag reset and stream joins between calls
+            loc2, rec2, _, corners2 = head(fm.cuda())
+            assert torch.equal(loc, loc2) and torch.equal(rec, rec2) and torch.equal(corners, corners2)
+        head.max_planes_per_call = 12           # chunked: several concurrent launches per call
+        head._cmax_cache.clear()
+        loc3, rec3, _, corners3 = head(fm.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(loc, loc3) and torch.equal(rec, rec3) and torch.equal(corners, corners3)
