@@ -31,6 +31,7 @@ import torch  # noqa: E402
 METRIC = "query-classes/sec at 1280px input"
 UNIT = "classes/s"
 D = 1024
+ASYNC_RESAMPLE_DEFAULT = False
 FM_SEED = 999          # the image feature map is replicated: same seed on every rank
 CLASS_SEED = 1234      # + rank (weak) / 4321 + owner rank (strong)
 
@@ -52,6 +53,8 @@ def parse_args():
                     help="run the five kernels class wave by class wave (this many classes per wave; 0 = all classes per kernel)")
     ap.add_argument("--concurrent-corr", type=int, default=-1,
                     help="SMs of the correlation kernel when it runs next to conv1 (0 = sequential kernels; -1 = library default)")
+    ap.add_argument("--async-resample", type=int, default=-1,
+                    help="1: K3 on a side stream (Os2dHead.submit) so that it overlaps the next image's tensor kernels; 0: in line")
     ap.add_argument("--cpu-sample-classes", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -414,21 +417,37 @@ def run_ours(args):
                 self.head.max_planes_per_call = args.wave_classes * B
             if args.concurrent_corr >= 0:
                 self.head.concurrent_corr_sms = args.concurrent_corr
-            self.handles = []
+            self.async_k3 = (args.async_resample == 1) if args.async_resample >= 0 else ASYNC_RESAMPLE_DEFAULT
+            if self.sharded is not None:
+                self.sharded.async_resample = self.async_k3
+            self.k3_events = []
+            self.last_event = None
 
         def step(self, fm_d):
             """One pass of the hot path; returns the (score, loc, corners) views [B,per,k,N] of THIS rank's block."""
             with torch.no_grad():
                 if self.sharded is None:
-                    loc, score, _, corners = self.head(fm_d)
+                    if self.async_k3:
+                        (loc, score, _, corners), ev = self.head.submit(fm_d)
+                        self.k3_events = self.k3_events[-3:] + [ev]
+                        self.last_event = ev
+                    else:
+                        loc, score, _, corners = self.head(fm_d)
+                        self.last_event = None
                     return score.view(B, self.per, 1, N), loc.view(B, self.per, 4, N), corners.view(B, self.per, 8, N)
                 h = self.sharded.submit(fm_d)
                 self.last = h
+                self.last_event = h.local_event
                 return h.local_views()
 
         def drain(self):
             if self.sharded is not None:
                 self.sharded.drain()
+            for ev in self.k3_events:
+                torch.cuda.current_stream().wait_event(ev)
+            self.k3_events = []
+            if getattr(self, "last_event", None) is not None:
+                torch.cuda.current_stream().wait_event(self.last_event)
 
         def timed(self, steps, warmup, with_stages=False, sampler=None):
             for _ in range(warmup):
@@ -484,6 +503,8 @@ def run_ours(args):
                     fm_free[k].record(s_main)
                     with torch.cuda.stream(s_d2h):
                         s_d2h.wait_event(fm_free[k])
+                        if self.last_event is not None:
+                            s_d2h.wait_event(self.last_event)      # K3 ran on its side stream
                         for dst, src in zip(out_host, srcs):
                             dst.copy_(src, non_blocking=True)
                             src.record_stream(s_d2h)
@@ -751,7 +772,8 @@ def run_ours(args):
             "dtype": "fp16 operands, fp32 accumulate (hi/lo-split weights)", "data": "synthetic",
             "config": dict(workload_config(args, world), gather=(args.gather if world > 1 else None),
                            wave_classes=(args.wave_classes or None),
-                           concurrent_corr_sms=(args.concurrent_corr if args.concurrent_corr >= 0 else "library default")),
+                           concurrent_corr_sms=(args.concurrent_corr if args.concurrent_corr >= 0 else "library default"),
+                           async_resample=((args.async_resample == 1) if args.async_resample >= 0 else ASYNC_RESAMPLE_DEFAULT)),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "parity": parity, "strong_c1000": strong, "pipeline": pipeline, "sustained": sustained,
             "e2e_detections": e2e_det, "host_link": host_link}

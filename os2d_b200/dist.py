@@ -132,6 +132,7 @@ class GatherHandle:
 
     def __init__(self, owner, slot, pending, B, H, W):
         self.owner, self.slot, self.pending, self.B, self.H, self.W = owner, slot, pending, B, H, W
+        self.local_event = None     # set when this rank's own block is produced on a side stream (async resample)
 
     def wait(self):
         if isinstance(self.pending, str):           # exchange still deferred (see ClassShardedHead.submit): start it now
@@ -181,6 +182,8 @@ class ClassShardedHead:
         # so the inbound NVLink writes overlap the tensor-bound conv1 instead of the L2-delivery-bound correlation kernel
         self.defer_exchange = True
         self._deferred = None
+        # copy-engine mode: launch K3 through Os2dHead.submit (side stream), so it overlaps the next image's tensor kernels
+        self.async_resample = False
 
     # ---- buffers: allocated once per (B, N) shape (collective for the symmetric modes), reused by every call ----
     def _ring(self, B, N, device):
@@ -234,6 +237,8 @@ class ClassShardedHead:
                 slots.barrier(k)
             slots.barrier(k)                                              # every rank's stores have landed everywhere
             return GatherHandle(self, slot, None, B, H, W)
+        ev_k3 = None
+
         def after_corr():
             if self._deferred is not None:
                 ev = torch.cuda.Event()
@@ -244,7 +249,11 @@ class ClassShardedHead:
             s_v, l_v, c_v = local_views(slot, self.rank)
             if getattr(self.head, "supports_out_views", False):
                 # the resample kernel writes straight into this rank's slice of the gather buffer (no staging copy)
-                self.head(feature_maps, out_views=(s_v[:, :n], l_v[:, :n], c_v[:, :n]), _after_corr=after_corr)
+                views = (s_v[:, :n], l_v[:, :n], c_v[:, :n])
+                if self.async_resample and mode == "copy_engine" and hasattr(self.head, "submit"):
+                    _, ev_k3 = self.head.submit(feature_maps, out_views=views, _after_corr=after_corr)
+                else:
+                    self.head(feature_maps, out_views=views, _after_corr=after_corr)
             else:
                 loc, score, _, corners = self.head(feature_maps)
                 s_v[:, :n].copy_(score.reshape(B, n, 1, N))
@@ -254,17 +263,22 @@ class ClassShardedHead:
         pending = None
         if self.world > 1:
             if mode == "copy_engine":
-                ev = torch.cuda.Event()
-                ev.record(torch.cuda.current_stream())
+                ev = ev_k3                         # this rank's block is complete when K3 is (side stream) ...
+                if ev is None:
+                    ev = torch.cuda.Event()        # ... or when the submitting stream gets here
+                    ev.record(torch.cuda.current_stream())
                 if self.defer_exchange:
                     handle = GatherHandle(self, slot, "deferred", B, H, W)
+                    handle.local_event = ev_k3
                     self._deferred = {"ring": ring, "k": k, "ev_head": ev, "handle": handle}
                     return handle
                 pending = ring["slots"].exchange(k, ev)
             else:
                 pending = all_gather_outputs(slot, self.group, async_op=True)
             ring["pending"][k] = pending
-        return GatherHandle(self, slot, pending, B, H, W)
+        handle = GatherHandle(self, slot, pending, B, H, W)
+        handle.local_event = ev_k3
+        return handle
 
     def _flush_deferred(self, extra_event=None):
         d = self._deferred

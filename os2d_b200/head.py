@@ -12,6 +12,7 @@ Inference only: the kernels implement the eval-mode forward (BatchNorm running s
 Calling the head with gradients required or BatchNorm in training mode raises - there is no PyTorch / CPU
 fallback path in this package.
 """
+import contextlib
 import ctypes
 import math
 import os
@@ -164,6 +165,17 @@ def _require_inference(t, module):
 
 
 _AUX_STREAMS = {}
+
+
+_K3_STREAMS = {}
+
+
+def _k3_stream(dev):
+    """Side stream of the asynchronous resample kernel (Os2dHead.submit), one per device."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _K3_STREAMS:
+        _K3_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _K3_STREAMS[key]
 
 
 def _aux_stream(dev):
@@ -507,8 +519,17 @@ class Os2dHead(nn.Module):
         self.profile_events.append((name, e0, e1))
         return rc
 
+    def submit(self, feature_maps, out_views=None, _after_corr=None):
+        """Pipelined form of ``forward`` for streams of images: identical results, but K3 (the L2-gather-bound resample / box
+        kernel, no tensor work, no shared memory) is launched on a side stream, so its blocks run in the register / issue
+        slack of the NEXT call's persistent tcgen05 kernels instead of after them.  Returns ``(outputs, event)``: outputs as
+        ``forward`` (None with ``out_views``), valid once ``event`` has completed - e.g.
+        ``torch.cuda.current_stream().wait_event(event)`` before consuming them."""
+        return self.forward(feature_maps, out_views=out_views, _after_corr=_after_corr, _async_resample=True)
+
     @_cabi.on_device_of
-    def forward(self, feature_maps, out_views=None, out_peers=None, _before_resample=None, _after_corr=None):
+    def forward(self, feature_maps, out_views=None, out_peers=None, _before_resample=None, _after_corr=None,
+                _async_resample=False):
         """feature_maps [B,D,H,W] -> (loc [B,C,4,H,W], rec [B,C,1,H,W], rec_transform_detached (same tensor under
         no-grad, head.py:400-402), corners [B,C,8,H,W]).  ``out_views`` (extension, default None): (score, loc, corners)
         strided views [B,C,k,H*W] to write into instead of fresh tensors; the call then returns None.
@@ -608,16 +629,33 @@ class Os2dHead(nn.Module):
                 launches = [(0, planes)]
             else:
                 launches = [(b, cc) for b in range(B)]
-            for b0, npl in launches:
-                _cabi.check(self._timed("resample", lib.os2d_resample_boxes, _cabi.ptr(rawvol[b0 * cc:]),
-                                        _cabi.ptr(params[b0 * cc:]), npl, P, H, W, inverse, float(gen.box_stride.w),
-                                        float(gen.box_stride.h), float(gen.box_size.w), float(gen.box_size.h),
-                                        ctypes.c_void_p(o_score[b0, c0].data_ptr()), ctypes.c_void_p(o_loc[b0, c0].data_ptr()),
-                                        ctypes.c_void_p(o_corners[b0, c0].data_ptr()), o_score.stride(1), o_loc.stride(1),
-                                        o_corners.stride(1), st), "os2d_resample_boxes")
-        if out_views is not None or out_peers is not None:
-            return None
-        return loc, score, score, corners
+            if _async_resample:
+                # K3 on the side stream, after this chunk's conv3; the workspaces it reads must not be handed out again by
+                # the allocator before it has run there
+                main = torch.cuda.current_stream()
+                k3s = _k3_stream(dev)
+                ev_c3 = torch.cuda.Event()
+                ev_c3.record(main)
+                k3s.wait_event(ev_c3)
+                for t in (rawvol, params) + ((score, loc, corners) if out_views is None else ()):
+                    t.record_stream(k3s)             # (caller-owned views are the caller's to keep alive)
+                k3_ctx, st_k3 = torch.cuda.stream(k3s), ctypes.c_void_p(k3s.cuda_stream)
+            else:
+                k3_ctx, st_k3 = contextlib.nullcontext(), st
+            with k3_ctx:
+                for b0, npl in launches:
+                    _cabi.check(self._timed("resample", lib.os2d_resample_boxes, _cabi.ptr(rawvol[b0 * cc:]),
+                                            _cabi.ptr(params[b0 * cc:]), npl, P, H, W, inverse, float(gen.box_stride.w),
+                                            float(gen.box_stride.h), float(gen.box_size.w), float(gen.box_size.h),
+                                            ctypes.c_void_p(o_score[b0, c0].data_ptr()), ctypes.c_void_p(o_loc[b0, c0].data_ptr()),
+                                            ctypes.c_void_p(o_corners[b0, c0].data_ptr()), o_score.stride(1), o_loc.stride(1),
+                                            o_corners.stride(1), st_k3), "os2d_resample_boxes")
+        outputs = None if (out_views is not None or out_peers is not None) else (loc, score, score, corners)
+        if _async_resample:
+            done = torch.cuda.Event()
+            done.record(_k3_stream(dev))
+            return outputs, done
+        return outputs
 
     @staticmethod
     @_cabi.on_device_of

@@ -40,7 +40,8 @@ def _worker(rank, world, port, ret, mode):
     ok = True
     with torch.no_grad():
         maps = [c.cuda() for c in cms]
-        sharded = bd.ClassShardedHead(maps, hc.create_os2d_head, gather=mode)
+        sharded = bd.ClassShardedHead(maps, hc.create_os2d_head, gather=mode.split("+")[0])
+        sharded.async_resample = mode.endswith("+async_k3")
         full = hc.create_os2d_head(maps)
         refs = [full(f.cuda()) for f in (fm, fm2)]
         # synchronous API, twice (buffer reuse)
@@ -75,7 +76,7 @@ def _spawn(fn, *args, world=2):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("mode", ["copy_engine", "fused", "nccl"])
+@pytest.mark.parametrize("mode", ["copy_engine", "copy_engine+async_k3", "fused", "nccl"])
 def test_class_sharded_head_equals_single_gpu(mode):
     ret = _spawn(_worker, mode)
     assert ret[0] and ret[1]

@@ -165,3 +165,37 @@ torch.save([loc.cpu(), rec.cpu(), cor.cpu()], sys.argv[1])
         outs.append(torch.load(path))
     for a, b in zip(*outs):
         assert torch.equal(a, b)        # same MMA order per accumulator element => bit-identical
+
+
+def test_submit_with_async_resample_equals_forward():
+    """Os2dHead.submit (K3 on a side stream, overlapping the next call's tensor kernels) == forward, bit for bit, also with
+    several submits in flight, chunked workspaces and caller-provided output views."""
+    from os2d_b200 import head as bh
+    from os2d_b200.structures import FeatureMapSize
+    tn = ho.random_transform_net(6, seed=3, spread=0.005)
+    cms, fm = synth_inputs(21, 2, 33, 29, [(15, 15), (12, 18), (19, 11), (15, 15), (10, 20), (15, 15), (9, 9)])
+    _, fm2 = synth_inputs(22, 2, 33, 29, [(15, 15)])
+    hc = bh.build_os2d_head_creator(False, True, True, FeatureMapSize(w=16, h=16), FeatureMapSize(w=16, h=16))
+    hc.aligner.parameter_regressor.load_state_dict(dict(tn), strict=False)
+    hc.eval()
+    with torch.no_grad():
+        head = hc.create_os2d_head([c.cuda() for c in cms])
+        refs = [head(f.cuda()) for f in (fm, fm2)]
+        pend = [head.submit(f.cuda()) for f in (fm, fm2, fm, fm2)]          # four calls in flight
+        for i, (out, ev) in enumerate(pend):
+            torch.cuda.current_stream().wait_event(ev)
+            for a, b in zip(out, refs[i % 2]):
+                assert torch.equal(a, b)
+        head.max_planes_per_call = 6                                        # several chunks, each with its own K3 launch
+        head._cmax_cache.clear()
+        out, ev = head.submit(fm.cuda())
+        ev.synchronize()
+        for a, b in zip(out, refs[0]):
+            assert torch.equal(a, b)
+        B, C, N = 2, 7, 33 * 29
+        buf = torch.zeros(B, C, 13, N, device="cuda")
+        none, ev = head.submit(fm2.cuda(), out_views=(buf[:, :, 0:1], buf[:, :, 1:5], buf[:, :, 5:13]))
+        assert none is None
+        ev.synchronize()
+        assert torch.equal(buf[:, :, 1:5].reshape(B, C, 4, 33, 29), refs[1][0])
+        assert torch.equal(buf[:, :, 0:1].reshape(B, C, 1, 33, 29), refs[1][1])
