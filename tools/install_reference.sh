@@ -14,5 +14,6 @@ PY
 rm -rf "$ROOT/baseline/_ref"
 mkdir -p "$ROOT/baseline"
 python -m pip install --no-index --no-build-isolation --no-deps --find-links /opt/wheelhouse --target "$ROOT/baseline/_ref" "$TMP" 2>&1 | tail -2
+cp "$SRC/main.py" "$ROOT/baseline/_ref/main.py"     # the reference's entry script, for the hooked dry run (tests/test_gpu_main_dry_run.py)
 rm -rf "$TMP"
 ls "$ROOT/baseline/_ref"
