@@ -62,3 +62,39 @@ def test_bad_arguments_fail_loudly():
             head(torch.rand(1, 64, 1, 8).cuda())                                 # 1-pixel-high map: reference yields NaN
         with pytest.raises(AssertionError):
             head(torch.rand(1, 128, 8, 8).cuda())                                # feature dimensionality mismatch
+
+
+def test_workspace_is_bounded_in_bytes():
+    """the per-call workspace (z / raw / h1 / h2 / params, ~1.47 KB per plane and location) is bounded in BYTES:
+    many class views on a large pyramid level are processed in class chunks, bit-identically to one big chunk."""
+    import torch
+    from os2d_b200 import head as bh
+    from os2d_b200.structures import FeatureMapSize
+    from oracle import head_oracle as ho
+    from _util import synth_inputs
+    tn = ho.random_transform_net(6, seed=2, spread=0.005)
+    cms, fm = synth_inputs(5, 2, 40, 36, [(15, 15)] * 9)
+    hc = bh.build_os2d_head_creator(False, True, True, FeatureMapSize(w=16, h=16), FeatureMapSize(w=16, h=16))
+    hc.aligner.parameter_regressor.load_state_dict(dict(tn), strict=False)
+    hc.eval()
+    with torch.no_grad():
+        head = hc.create_os2d_head([c.cuda() for c in cms])
+        ref = head(fm.cuda())
+        N, B, P = 40 * 36, 2, 6
+        per_plane = N * (30 * 16 + 225 * 2 + 256 + 256 + 4 * P)
+        assert head._classes_per_chunk(B, N, P, fm.cuda().device) == 9 or head._classes_per_chunk(B, N, P, fm.cuda().device) >= 9
+        head.workspace_bytes = 7 * per_plane                       # room for 7 planes = 3 classes of a 2-image batch
+        head._cmax_cache.clear()
+        assert head._classes_per_chunk(B, N, P, fm.cuda().device) == 3
+        out = head(fm.cuda())
+        head.workspace_bytes = 1                                   # degenerate budget: one class at a time, never zero
+        head._cmax_cache.clear()
+        assert head._classes_per_chunk(B, N, P, fm.cuda().device) == 1
+        out1 = head(fm.cuda())
+    for a, b, c in zip(ref, out, out1):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    # what the default budget does for the case of the advice: 1000 views on a 150x150 level
+    free, _ = torch.cuda.mem_get_info()
+    big = head._classes_per_chunk.__func__(type("H", (), {"max_planes_per_call": 4096, "workspace_bytes": None, "_cmax_cache": {}})(),
+                                           1, 150 * 150, 6, fm.cuda().device)
+    assert big * 150 * 150 * 1466 <= free

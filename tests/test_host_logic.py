@@ -161,3 +161,24 @@ def test_build_loc_targets_matches_oracle_encoding():
     anchor = BoxList(torch.tensor([[8 - 120., 8 - 120, 8 + 120, 8 + 120]]), FeatureMapSize(w=2, h=2))
     enc = Os2dBoxCoder.build_loc_targets(cls_box, anchor)
     assert torch.allclose(enc[0], loc[0, :, 0, 0], atol=1e-5)
+
+
+def test_inverse_transform_probe_accepts_resizes_and_refuses_flips():
+    """decode_pyramid applies the inverse box transform as a per-axis rescale; a transform that does anything else
+    (flip, crop) must be refused instead of silently mis-placing boxes."""
+    import pytest
+    from os2d_b200.box_coder import _probe_transform_target, make_resize_transform
+    from os2d_b200.structures import BoxList, FeatureMapSize
+    img = FeatureMapSize(w=320, h=240)
+    assert _probe_transform_target(make_resize_transform(FeatureMapSize(w=640, h=480)), img) == FeatureMapSize(w=640, h=480)
+    # a plain callable that resizes with different ratios per axis (BoxList.resize's second branch)
+    t = _probe_transform_target(lambda b: b.resize(FeatureMapSize(w=160, h=480)), img)
+    assert (t.w, t.h) == (160, 480)
+
+    def hflip(boxes):
+        b = boxes.bbox_xyxy.clone()
+        w = boxes.image_size.w
+        out = BoxList(torch.stack([w - b[:, 2], b[:, 1], w - b[:, 0], b[:, 3]], dim=1), boxes.image_size)
+        return out
+    with pytest.raises(NotImplementedError):
+        _probe_transform_target(hflip, img)
