@@ -5,10 +5,13 @@ Os2dBoxCoder.decode_pyramid :448-536, _nms_box_lists :424-437, build_loc_targets
 os2d/structures/bounding_box.py nms :344-387.  Training-only members (encode, remap_anchor_targets,
 get_box_to_cut_anchor) are out of scope of the hot path and not provided.
 
-The reference loops in Python over classes x levels with tiny kernels; here one decode launch handles all
-classes of a level (csrc/postproc.cu decode_kernel) and one NMS launch handles all (label, chunk) segments
-(nms_kernel), reproducing the chunk-of-10000 / iterate-to-fixpoint semantics of the reference exactly.
+The reference loops in Python over classes x levels with tiny kernels; here ``decode_pyramid`` is two launches for any
+number of classes, levels and candidates (csrc/detect.cu: one CTA per real label decodes, filters, orders and runs the
+chunk-of-10000 / iterate-to-fixpoint NMS of the reference exactly; a second kernel writes the survivors).  The staged
+round-1 form (decode kernel per level + torch ordering + segment NMS kernel per pass) stays as ``decode_pyramid_staged``
+(ablation, independent check) and behind ``nms()`` for plain BoxLists.
 """
+import ctypes
 import math
 
 import torch
@@ -157,6 +160,19 @@ def _segmented_chunked_nms(xyxy, scores, cand, counts, iou_thr):
     return torch.cat(result_per_label) if n_labels > 0 else cand
 
 
+class PendingDetections:
+    """Handle of Os2dBoxCoder.decode_pyramid_async: ``result()`` (once) finishes the call and returns the BoxList."""
+
+    def __init__(self, finish):
+        self._finish, self._out = finish, None
+
+    def result(self):
+        if self._finish is not None:
+            self._out = self._finish()
+            self._finish = None
+        return self._out
+
+
 class Os2dBoxCoder:
     """Inference side of the reference box coder (box_coder.py:169-189, 448-536): anchors from the image-level
     box grid generator and the network's feature-map-size function, decode + NMS across the pyramid."""
@@ -211,11 +227,24 @@ class Os2dBoxCoder:
         keep = keep[torch.sort(sc, dim=0, descending=True)[1]]
         return boxes[keep]
 
-    @_cabi.on_device_of
     def decode_pyramid(self, loc_scores_pyramid, cls_scores_pyramid, img_size_pyramid, class_ids,
                        nms_score_threshold=0.0, nms_iou_threshold=0.3, inverse_box_transforms=None,
                        transform_corners_pyramid=None):
-        """Same contract as box_coder.py:448-536.  loc [C,4,N_l], cls [C,N_l] (and corners [C,8,N_l]) per level ->
+        """Same contract as box_coder.py:448-536 (see decode_pyramid_async, of which this is the synchronous form)."""
+        return self.decode_pyramid_async(loc_scores_pyramid, cls_scores_pyramid, img_size_pyramid, class_ids,
+                                         nms_score_threshold=nms_score_threshold, nms_iou_threshold=nms_iou_threshold,
+                                         inverse_box_transforms=inverse_box_transforms,
+                                         transform_corners_pyramid=transform_corners_pyramid).result()
+
+    @_cabi.on_device_of
+    def decode_pyramid_async(self, loc_scores_pyramid, cls_scores_pyramid, img_size_pyramid, class_ids,
+                             nms_score_threshold=0.0, nms_iou_threshold=0.3, inverse_box_transforms=None,
+                             transform_corners_pyramid=None):
+        """Launches the decode + NMS kernel and returns a handle; ``handle.result()`` reads the detection count back (the only
+        host synchronisation - it waits for THIS kernel only, work enqueued in between keeps the GPU busy), launches the
+        gather kernel and returns the BoxList.  Pipelines of images call result() of image i after submitting image i+1.
+
+        Same contract as box_coder.py:448-536.  loc [C,4,N_l], cls [C,N_l] (and corners [C,8,N_l]) per level ->
         BoxList with fields scores, labels, default_boxes (, transform_corners).  ``inverse_box_transforms`` may be
         reference TransformList objects that only resize (their effect is obtained by probing them with a
         box list) or anything with a ``target_size`` / callable returning a resized BoxList.
@@ -280,30 +309,51 @@ class Os2dBoxCoder:
                                      _cabi.ptr(keys), _cabi.ptr(out_ids), _cabi.ptr(counts), _cabi.ptr(offsets),
                                      _cabi.ptr(done), st)
         _cabi.check(rc, "os2d_detect_pyramid")
-        total = int(offsets[n_labels].item())                     # the one host synchronisation: number of detections
-        boxes = torch.empty(total, 4, dtype=torch.float32, device=device)
-        scores = torch.empty(total, dtype=torch.float32, device=device)
-        labels = torch.empty(total, dtype=torch.long, device=device)
-        anchors = torch.empty(total, 4, dtype=torch.float32, device=device)
-        corners = torch.empty(total, 8, dtype=torch.float32, device=device) if have_corners else None
-        if total > 0:
-            rc = lib.os2d_gather_detections(levels, L, num_classes, _cabi.ptr(view_off), n_labels, *grid_args,
-                                            _cabi.ptr(out_ids), _cabi.ptr(counts), _cabi.ptr(offsets), _cabi.ptr(label_values),
-                                            _cabi.ptr(boxes), _cabi.ptr(scores), _cabi.ptr(labels), _cabi.ptr(anchors),
-                                            _cabi.ptr(corners), st)
-            _cabi.check(rc, "os2d_gather_detections")
-        # workspaces and fp32 copies stay referenced (`alive`, locals) until both launches are enqueued; the caching allocator
-        # hands their blocks out again in stream order on this same stream, so no record_stream is needed
-        del alive
-        out = BoxList(boxes, out_size if out_size is not None else img_size_pyramid[0])
-        out.add_field("scores", scores)
-        out.add_field("default_boxes", BoxList(anchors, out.image_size))
-        out.add_field("labels", labels)
-        if have_corners:
-            out.add_field("transform_corners", corners)
-        if self.do_nms_across_classes and len(out) > 0:
-            out = self._nms_box_lists([out], nms_iou_threshold)
-        return out
+        count_host = self._pinned_count()
+        count_host.copy_(offsets[n_labels:n_labels + 1], non_blocking=True)
+        counted = torch.cuda.Event()
+        stream = torch.cuda.current_stream()
+        counted.record(stream)
+        out_size = out_size if out_size is not None else img_size_pyramid[0]
+
+        def finish():
+            counted.synchronize()                                  # the one host synchronisation: number of detections
+            total = int(count_host[0])
+            with torch.cuda.device(device), torch.cuda.stream(stream):
+                boxes = torch.empty(total, 4, dtype=torch.float32, device=device)
+                scores = torch.empty(total, dtype=torch.float32, device=device)
+                labels = torch.empty(total, dtype=torch.long, device=device)
+                anchors = torch.empty(total, 4, dtype=torch.float32, device=device)
+                corners = torch.empty(total, 8, dtype=torch.float32, device=device) if have_corners else None
+                if total > 0:
+                    rc = lib.os2d_gather_detections(levels, L, num_classes, _cabi.ptr(view_off), n_labels, *grid_args,
+                                                    _cabi.ptr(out_ids), _cabi.ptr(counts), _cabi.ptr(offsets),
+                                                    _cabi.ptr(label_values), _cabi.ptr(boxes), _cabi.ptr(scores), _cabi.ptr(labels),
+                                                    _cabi.ptr(anchors), _cabi.ptr(corners), ctypes.c_void_p(stream.cuda_stream))
+                    _cabi.check(rc, "os2d_gather_detections")
+            # the inputs' fp32 copies and the workspaces (`alive`, closure) stay referenced until both launches are enqueued;
+            # the caching allocator hands their blocks out again in stream order on this same stream
+            alive.clear()
+            out = BoxList(boxes, out_size)
+            out.add_field("scores", scores)
+            out.add_field("default_boxes", BoxList(anchors, out.image_size))
+            out.add_field("labels", labels)
+            if have_corners:
+                out.add_field("transform_corners", corners)
+            if self.do_nms_across_classes and len(out) > 0:
+                out = self._nms_box_lists([out], nms_iou_threshold)
+            return out
+
+        return PendingDetections(finish)
+
+    def _pinned_count(self):
+        """Small ring of pinned int32 scalars for the asynchronous read-back of the detection count."""
+        ring = self.__dict__.setdefault("_count_ring", [])
+        if len(ring) < 16:
+            ring.append(torch.empty(1, dtype=torch.int32).pin_memory())
+            return ring[-1]
+        self.__dict__["_count_pos"] = (self.__dict__.get("_count_pos", 0) + 1) % 16
+        return ring[self.__dict__["_count_pos"]]
 
     def _label_tables(self, class_ids, device):
         """Device tables of the label structure, cached per class-id tuple: views of real label i (set order, box_coder.py:483)

@@ -380,9 +380,8 @@ class ClassShardedDetector:
         self.head = head_factory([class_feature_maps[i] for i in self.view_index]) if self.view_index else None
 
     def local_detections(self, feature_maps_pyramid, img_size_pyramid, nms_score_threshold=0.0, nms_iou_threshold=0.3,
-                         inverse_box_transforms=None):
+                         inverse_box_transforms=None, _async=False):
         """Decode + NMS of this rank's labels for ONE image given as a pyramid of [1,D,H_l,W_l] feature maps."""
-        from .structures import BoxList
         if self.head is None:
             return None
         loc_p, cls_p, cor_p = [], [], []
@@ -393,17 +392,25 @@ class ClassShardedDetector:
             loc_p.append(loc[0].view(C, 4, n))
             cls_p.append(score[0].view(C, n))
             cor_p.append(corners[0].view(C, 8, n))
-        dets = self.box_coder.decode_pyramid(loc_p, cls_p, img_size_pyramid, self.class_ids,
-                                             nms_score_threshold=nms_score_threshold, nms_iou_threshold=nms_iou_threshold,
-                                             inverse_box_transforms=inverse_box_transforms, transform_corners_pyramid=cor_p)
-        assert isinstance(dets, BoxList)
-        return dets
+        decode = self.box_coder.decode_pyramid_async if _async else self.box_coder.decode_pyramid
+        return decode(loc_p, cls_p, img_size_pyramid, self.class_ids, nms_score_threshold=nms_score_threshold,
+                      nms_iou_threshold=nms_iou_threshold, inverse_box_transforms=inverse_box_transforms,
+                      transform_corners_pyramid=cor_p)
+
+    def submit(self, feature_maps_pyramid, img_size_pyramid, **kw):
+        """Enqueue the heads and the decode + NMS kernel of one image; ``result(handle)`` finishes it.  Submitting image i+1
+        before asking for the result of image i keeps the GPU busy while the host waits for image i's detection count."""
+        pending = self.local_detections(feature_maps_pyramid, img_size_pyramid, _async=True, **kw)
+        return pending, feature_maps_pyramid[0].device, img_size_pyramid, kw
 
     def forward(self, feature_maps_pyramid, img_size_pyramid, **kw):
+        return self.result(self.submit(feature_maps_pyramid, img_size_pyramid, **kw))
+
+    def result(self, handle):
         from .structures import BoxList
         from .box_coder import _probe_transform_target
-        dets = self.local_detections(feature_maps_pyramid, img_size_pyramid, **kw)
-        device = feature_maps_pyramid[0].device
+        pending, device, img_size_pyramid, kw = handle
+        dets = pending.result() if pending is not None else None
         if dets is not None:
             rows = torch.cat([dets.bbox_xyxy, dets.get_field("scores")[:, None],
                               dets.get_field("labels").to(torch.int32).view(torch.float32)[:, None],     # bit cast

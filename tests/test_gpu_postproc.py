@@ -178,3 +178,22 @@ def test_fused_decode_nms_no_candidates_and_no_corners():
     some = _coder().decode_pyramid(loc, cls, sizes, [0, 1, 2], nms_score_threshold=0.5)
     _same_detections(some, _coder().decode_pyramid_staged(loc, cls, sizes, [0, 1, 2], nms_score_threshold=0.5))
     assert not some.has_field("transform_corners")
+
+
+def test_decode_pyramid_async_handles_in_flight():
+    """decode_pyramid_async: several calls submitted before any result is read (the pipelined use) give the synchronous results."""
+    from os2d_b200.structures import FeatureMapSize
+    g = torch.Generator().manual_seed(9)
+    coder = _coder()
+    sizes = [FeatureMapSize(w=640, h=480)]
+    calls = []
+    for k in range(4):
+        loc = [torch.randn(5, 4, 40 * 30, generator=g).cuda()]
+        cls = [torch.rand(5, 40 * 30, generator=g).cuda()]
+        calls.append((loc, cls))
+    sync = [coder.decode_pyramid(loc, cls, sizes, [2, 0, 1, 2, 4], nms_score_threshold=0.3) for loc, cls in calls]
+    pend = [coder.decode_pyramid_async(loc, cls, sizes, [2, 0, 1, 2, 4], nms_score_threshold=0.3) for loc, cls in calls]
+    for p, ref in zip(reversed(pend), reversed(sync)):                   # any order of completion
+        got = p.result()
+        assert got is p.result()                                         # idempotent
+        _same_detections(got, ref)
