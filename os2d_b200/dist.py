@@ -178,9 +178,11 @@ class ClassShardedHead:
         self.depth = depth
         self._rings = {}
         self._step = 0
-        # copy-engine mode: the pushes of image i are enqueued only once K1 of image i+1 has been launched (and wait for it),
-        # so the inbound NVLink writes overlap the tensor-bound conv1 instead of the L2-delivery-bound correlation kernel
-        self.defer_exchange = True
+        # copy-engine mode, optional: enqueue the pushes of image i only once K1 of image i+1 has been launched (and wait for
+        # it), so that the inbound NVLink writes overlap conv1 instead of the correlation kernel.  Measured at 8 GPUs: K1 is
+        # back at 0.25 ms (from 0.32), but the two all-rank barriers now also wait for every rank's K1 and the step gets
+        # LONGER (2.11 -> 2.39 ms, profiles/r02_bench_n8_*_run2_deferred_exchange.json) - so it is off by default.
+        self.defer_exchange = False
         self._deferred = None
         # copy-engine mode: launch K3 through Os2dHead.submit (side stream), so it overlaps the next image's tensor kernels
         self.async_resample = False
