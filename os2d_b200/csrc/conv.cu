@@ -117,7 +117,6 @@ __global__ void __launch_bounds__(THREADS, 1) conv_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int tiles_per_plane = P.TY * P.TXP;
   pdl_wait();          // the input volume is the previous kernel's output
 
   // Strip staggering: with 2 strips the first and the last 16-channel sub-chunk are issued strip by strip (their weight rows

@@ -1,6 +1,6 @@
 """2-GPU probe: symmetric memory rendezvous, peer tensor views, copy-engine push bandwidth, device barrier, NCCL all-gather
 timing.  Run under torchrun --nproc-per-node 2."""
-import os, time, json
+import os, json
 import torch
 import torch.distributed as dist
 
