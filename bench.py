@@ -609,6 +609,7 @@ def run_ours(args):
     ms_total, stage_avg, launches = weak.timed(args.steps, args.warmup, with_stages=True, sampler=sampler)
     clocks = sampler.stop() if rank == 0 else None
     value = B * C * world * args.steps / (ms_total * 1e-3)
+    gather_used = weak.sharded.transport() if weak.sharded is not None else None
     e2e = weak.e2e(args.steps, args.warmup)
     parity = weak.parity()
     e2e_det = None
@@ -782,7 +783,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16 operands, fp32 accumulate (hi/lo-split weights)", "data": "synthetic",
-            "config": dict(workload_config(args, world), gather=(args.gather if world > 1 else None),
+            "config": dict(workload_config(args, world), gather=(gather_used if world > 1 else None),
                            wave_classes=(args.wave_classes or None),
                            concurrent_corr_sms=(args.concurrent_corr if args.concurrent_corr >= 0 else "library default"),
                            async_resample=((args.async_resample == 1) if args.async_resample >= 0 else ASYNC_RESAMPLE_DEFAULT)),

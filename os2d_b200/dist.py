@@ -200,8 +200,24 @@ class ClassShardedHead:
             per = padded_block(self.num_classes, self.world)
             ring = {"mode": mode, "pending": [None] * self.depth, "ptrs": None}
             if mode in ("copy_engine", "fused"):
-                ring["slots"] = SymmetricSlots(self.depth, self.world, self.rank, (B, per, OUT_PLANES, N), torch.float32,
-                                               device, self.group)
+                # symmetric memory needs NVLink peer mapping between all ranks; where the platform refuses it, every rank
+                # agrees (one all-reduce) to run this ring over the NCCL transport instead - loudly, never silently
+                slots, err = None, None
+                try:
+                    slots = SymmetricSlots(self.depth, self.world, self.rank, (B, per, OUT_PLANES, N), torch.float32,
+                                           device, self.group)
+                except Exception as e:   # noqa: BLE001
+                    err = e
+                ok = torch.tensor([0 if slots is None else 1], dtype=torch.int32, device=device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+                if int(ok.item()) == 0:
+                    import warnings
+                    warnings.warn("os2d_b200.dist: symmetric memory is not available on this platform ({}); the '{}' gather "
+                                  "runs over NCCL instead".format(err, mode))
+                    mode = ring["mode"] = "nccl"
+                    slots = None
+            if mode in ("copy_engine", "fused"):
+                ring["slots"] = slots
                 ring["buffer"] = ring["slots"].buffer
                 if mode == "fused":
                     ring["ptrs"] = [ring["slots"].peer_slot_pointers(k) for k in range(self.depth)]
@@ -291,6 +307,10 @@ class ClassShardedHead:
         d["ring"]["pending"][d["k"]] = ev
         d["handle"].pending = ev
 
+    def transport(self):
+        """The gather transports actually in use, per (B, N) ring: 'copy_engine' | 'fused' | 'nccl'."""
+        return sorted(set(r["mode"] for r in self._rings.values()))
+
     def drain(self):
         """Wait (stream-level) for every gather still in flight."""
         self._flush_deferred()
@@ -326,18 +346,36 @@ class ShardedUpload:
         self.numel = numel
         self.part = -(-numel // self.world)
         self.part = -(-self.part // 64) * 64
+        self.slots = None
+        self.full_copy = self.world == 1               # every rank copies the whole tensor itself
         if self.world > 1:
-            self.slots = SymmetricSlots(depth, self.world, self.rank, (self.part,), dtype, device, group)
+            err = None
+            try:
+                self.slots = SymmetricSlots(depth, self.world, self.rank, (self.part,), dtype, device, group)
+            except Exception as e:   # noqa: BLE001
+                err = e
+            ok = torch.tensor([0 if self.slots is None else 1], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:                     # agreed by all ranks: no peer mapping here, upload everything locally
+                import warnings
+                warnings.warn("os2d_b200.dist.ShardedUpload: symmetric memory is not available ({}); every rank uploads the "
+                              "whole tensor".format(err))
+                self.slots, self.full_copy = None, True
+        if self.slots is not None:
             self.flat = [self.slots.buffer[k].view(-1) for k in range(depth)]
         else:
-            self.slots = None
-            self.flat = [torch.empty(self.part, dtype=dtype, device=device) for _ in range(depth)]
+            self.flat = [torch.empty(max(self.part, numel), dtype=dtype, device=device) for _ in range(depth)]
             self.stream = torch.cuda.Stream(device=device)
         self._step = 0
 
-    def bytes_per_rank(self):
+    def _own_range(self):
+        if self.full_copy:
+            return 0, self.numel
         lo = min(self.rank * self.part, self.numel)
-        hi = min(lo + self.part, self.numel)
+        return lo, min(lo + self.part, self.numel)
+
+    def bytes_per_rank(self):
+        lo, hi = self._own_range()
         return (hi - lo) * torch.empty(0, dtype=self.dtype).element_size()
 
     def upload(self, host_pinned, after_event=None):
@@ -345,8 +383,7 @@ class ShardedUpload:
         k = self._step % self.depth
         self._step += 1
         src = host_pinned.view(-1)
-        lo = min(self.rank * self.part, self.numel)
-        hi = min(lo + self.part, self.numel)
+        lo, hi = self._own_range()
         out = self.flat[k][:self.numel].view(self.shape)
         if self.slots is None:
             with torch.cuda.stream(self.stream):
