@@ -182,3 +182,18 @@ def test_inverse_transform_probe_accepts_resizes_and_refuses_flips():
         return out
     with pytest.raises(NotImplementedError):
         _probe_transform_target(hflip, img)
+
+
+def test_packed_feature_maps_mirror_the_tensor_interface():
+    """head.PackedFeatureMaps stands in for the [B,D,H,W] tensor the reference passes around: shape / size / device / batch slicing."""
+    import pytest
+    from os2d_b200.head import PackedFeatureMaps
+    packed = torch.zeros(3, 5 * 7, 64, dtype=torch.float16)
+    fm = PackedFeatureMaps(packed, 5, 7)
+    assert tuple(fm.shape) == (3, 64, 5, 7) and fm.size(1) == 64 and fm.size() == fm.shape and fm.requires_grad is False
+    one = fm[1]
+    assert tuple(one.shape) == (1, 64, 5, 7) and tuple(fm[1:3].shape) == (2, 64, 5, 7)
+    with pytest.raises(AssertionError):
+        PackedFeatureMaps(packed.float(), 5, 7)            # the operand is fp16 by construction
+    with pytest.raises(AssertionError):
+        PackedFeatureMaps(packed, 5, 8)                    # H * W must match the packed rows
