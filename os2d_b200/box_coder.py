@@ -319,6 +319,7 @@ class Os2dBoxCoder:
         def finish():
             counted.synchronize()                                  # the one host synchronisation: number of detections
             total = int(count_host[0])
+            self.__dict__.setdefault("_count_free", []).append(count_host)       # back to the pool of pinned scalars
             with torch.cuda.device(device), torch.cuda.stream(stream):
                 boxes = torch.empty(total, 4, dtype=torch.float32, device=device)
                 scores = torch.empty(total, dtype=torch.float32, device=device)
@@ -347,13 +348,10 @@ class Os2dBoxCoder:
         return PendingDetections(finish)
 
     def _pinned_count(self):
-        """Small ring of pinned int32 scalars for the asynchronous read-back of the detection count."""
-        ring = self.__dict__.setdefault("_count_ring", [])
-        if len(ring) < 16:
-            ring.append(torch.empty(1, dtype=torch.int32).pin_memory())
-            return ring[-1]
-        self.__dict__["_count_pos"] = (self.__dict__.get("_count_pos", 0) + 1) % 16
-        return ring[self.__dict__["_count_pos"]]
+        """A pinned int32 scalar for the asynchronous read-back of the detection count: taken from a pool, returned by
+        ``finish`` (any number of handles may be in flight; a handle that is dropped unread just keeps its scalar)."""
+        free = self.__dict__.setdefault("_count_free", [])
+        return free.pop() if free else torch.empty(1, dtype=torch.int32).pin_memory()
 
     def _label_tables(self, class_ids, device):
         """Device tables of the label structure, cached per class-id tuple: views of real label i (set order, box_coder.py:483)
